@@ -1,0 +1,140 @@
+"""Pins oracle/srgd_oracle.py against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py; /root/reference/model.py).  CPU only.
+
+Tolerances: the fixtures were computed on the build container's CPU in fp32; re-running the same
+fp32 math on another CPU (different oneDNN/MKL kernels, thread counts) reorders sums, so exact
+equality is not expected.  2e-4 abs on O(1) activations / eps; scalars to 1e-6 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import srgd_oracle as O
+
+SPECS = {"tiny": (O.UnetSpec(dim=16), 11), "mid": (O.UnetSpec(dim=64), 22), "full": (O.UnetSpec(dim=128), 1234)}
+ATOL = 2e-4
+
+
+def _load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_param_layout_full():
+    shapes = O.param_shapes(O.UnetSpec())
+    assert len(shapes) == 280
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    assert n == 137_569_939
+    assert shapes["model.init_conv.weight"] == (128, 6, 7, 7)
+    assert shapes["model.ups.0.3.net.0.weight"] == (2048, 1024, 1, 1)
+    assert shapes["model.final_conv.weight"] == (3, 128, 1, 1)
+
+
+def test_schedule_scalars(golden_dir):
+    g = _load(golden_dir, "scalars_250")
+    steps = torch.linspace(1., 0., 251)
+    assert torch.equal(steps, T(g["steps"]))
+    tab = T(g["table"])
+    for i in range(250):
+        s = O.step_scalars(steps[i], steps[i + 1])
+        row = torch.stack([s["log_snr"], s["log_snr_next"], s["c"], s["alpha"], s["sigma"],
+                           s["alpha_next"], s["var"]])
+        torch.testing.assert_close(row, tab[i], rtol=1e-6, atol=1e-7)
+    assert abs(float(tab[0, 3]) - 6.74e-3) < 1e-4               # alpha_0, SURVEY.md §7
+
+
+def test_tile_geometry(golden_dir):
+    geo = json.load(open(os.path.join(golden_dir, "geometry.json")))
+    for e in geo:
+        h, w = e["hw"]
+        coord, pad = O.get_coord_and_pad(h, w)
+        assert list(coord) == e["coord"] and list(pad) == e["pad"]
+        H, W = h + pad[2] + pad[3], w + pad[0] + pad[1]
+        c0 = O.get_coords(H, W, 256, 256, 0)
+        c1 = c0 if (H <= 256 and W <= 256) else O.get_coords(H - 256, W - 256, 256, 256, 128)
+        assert [list(c) for c in c0] == e["c0"] and [list(c) for c in c1] == e["c1"]
+        area, apad = O.get_area(c1, H, W)
+        assert list(area) == e["area"] and list(apad) == e["apad"]
+
+
+@pytest.mark.parametrize("tag", ["tiny", "mid", "full"])
+def test_unet_forward(golden_dir, tag):
+    spec, seed = SPECS[tag]
+    g = _load(golden_dir, f"unet_{tag}")
+    sd = O.make_state_dict(spec, seed)
+    x, cond, lsnr, labels = T(g["x"]), T(g["cond"]), T(g["log_snr"]), T(g["labels"])
+    taps = {}
+    eps = O.unet_forward(sd, spec, x, lsnr, labels, cond, taps=taps)
+    torch.testing.assert_close(eps, T(g["eps_label_cond"]), rtol=0, atol=ATOL)
+    torch.testing.assert_close(O.unet_forward(sd, spec, x, lsnr, None, cond), T(g["eps_nolabel_cond"]), rtol=0, atol=ATOL)
+    torch.testing.assert_close(O.unet_forward(sd, spec, x, lsnr, labels, None), T(g["eps_label_nocond"]), rtol=0, atol=ATOL)
+    torch.testing.assert_close(O.unet_forward(sd, spec, x, lsnr, labels[:1], cond), T(g["eps_label1_cond"]), rtol=0, atol=ATOL)
+    for name in ["init_conv", "downs.0.0", "downs.0.2", "downs.3.2", "mid_block1", "ups.0.3", "final_res_block"]:
+        ref = T(g["act_" + name])
+        a = taps[name]
+        if name in ("downs.0.2", "downs.3.2"):
+            continue          # reference hook captures attn(x) (pre-residual); oracle tap is attn(x)+x
+        sub = a[:, ::max(1, a.shape[1] // 8), ::4, ::4]
+        torch.testing.assert_close(sub, ref, rtol=0, atol=ATOL)
+
+
+def test_p_sample_teacher_forced(golden_dir):
+    spec, seed = SPECS["mid"]
+    g = _load(golden_dir, "p_sample_mid")
+    sd = O.make_state_dict(spec, seed)
+    steps = torch.linspace(1., 0., 251)
+    cond, label = T(g["cond"]), T(g["label"])
+    for ci in range(int(g["ncases"])):
+        i, cs, ccs = g[f"c{ci}_meta"]
+        i = int(i)
+        x, noise = T(g[f"c{ci}_x"]), T(g[f"c{ci}_noise"])
+        img, x0 = O.p_sample(sd, spec, x, steps[i], cond, label, float(cs), float(ccs), steps[i + 1], noise=noise)
+        # x0 = (x - sigma eps)/alpha amplifies eps error by sigma/alpha (148x at step 0) before the clamp
+        torch.testing.assert_close(img, T(g[f"c{ci}_img"]), rtol=0, atol=2e-4)
+        amp = float(O.step_scalars(steps[i], steps[i + 1])["sigma"] / O.step_scalars(steps[i], steps[i + 1])["alpha"])
+        torch.testing.assert_close(x0, T(g[f"c{ci}_x0"]), rtol=0, atol=max(2e-4, 2e-5 * amp))
+        mean, var, _ = O.p_mean_variance(sd, spec, x, steps[i], cond, label, float(cs), float(ccs), steps[i + 1])
+        torch.testing.assert_close(mean, T(g[f"c{ci}_mean"]), rtol=0, atol=2e-4)
+        torch.testing.assert_close(var, T(g[f"c{ci}_var"]), rtol=1e-6, atol=1e-9)
+
+
+def test_both_scales_raise():
+    spec, seed = SPECS["tiny"]
+    sd = O.make_state_dict(spec, seed)
+    x = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(NotImplementedError):
+        O.p_mean_variance(sd, spec, x, torch.tensor(1.0), x, torch.tensor([0]), 2.0, 2.0, torch.tensor(0.9))
+    with pytest.raises(AssertionError):
+        O.unet_forward(sd, spec, torch.zeros(1, 3, 36, 64), torch.zeros(1))
+
+
+@pytest.mark.parametrize("tag", ["tiny", "mid"])
+def test_sample_free_running(golden_dir, tag):
+    spec, seed = SPECS[tag]
+    g = _load(golden_dir, f"sample_{tag}")
+    sd = O.make_state_dict(spec, seed)
+    torch.manual_seed(int(g["seed"]))
+    img = O.sample(sd, spec, 2, T(g["cond01"]), class_label=T(g["label"]), class_cond_scale=float(g["ccs"]),
+                   num_sample_steps=int(g["nsteps"]), image_size=64)
+    torch.testing.assert_close(img, T(g["img"]), rtol=0, atol=5e-4)
+
+
+def test_tiled_sample(golden_dir):
+    spec, seed = SPECS["tiny"]
+    sd = O.make_state_dict(spec, seed)
+    g = _load(golden_dir, "tiled_tiny_single")
+    torch.manual_seed(int(g["seed"]))
+    img = O.tiled_sample(sd, spec, int(g["batch_size"]), T(g["cond01"]), None, num_sample_steps=int(g["nsteps"]))
+    torch.testing.assert_close(img, T(g["img"]), rtol=0, atol=5e-4)
+    g = _load(golden_dir, "tiled_tiny")
+    torch.manual_seed(int(g["seed"]))
+    img = O.tiled_sample(sd, spec, int(g["batch_size"]), T(g["cond01"]), T(g["label"]),
+                         class_cond_scale=float(g["ccs"]), num_sample_steps=int(g["nsteps"]))
+    assert img.shape == (1, 3, 272, 264)
+    torch.testing.assert_close(img, T(g["img"]), rtol=0, atol=5e-4)
