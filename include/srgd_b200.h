@@ -1,0 +1,236 @@
+/*
+ * srgd_b200 -- C-ABI of the B200-native (sm_100a) Real-SRGD sampling hot path.
+ *
+ * The reference (yahoojapan/srgd) has no FFI: its hot path is Python/PyTorch
+ * (model.py).  Each entry point below replaces the reference code it cites
+ * (paths relative to the reference checkout); the Python host in `srgd_b200/`
+ * binds them with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SRGD_E_* code; the text
+ *     of the last failure on the calling thread is srgd_last_error();
+ *   - pointers named *_dev / documented "device" are CUDA device pointers owned
+ *     by the caller (torch tensors via .data_ptr()); nothing is allocated,
+ *     freed or synchronised inside (workspaces are passed in);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - activations between kernels are bf16 NHWC ("pixel-major": [B][H][W][C]);
+ *     sampler state, eps, noise and images are fp32 NCHW exactly like the
+ *     reference tensors;
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry
+ *     point fails with SRGD_E_DEVICE.
+ */
+#ifndef SRGD_B200_H
+#define SRGD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRGD_B200_VERSION 100
+
+enum {
+  SRGD_OK = 0,
+  SRGD_E_ARG = -1,      /* invalid argument / unsupported shape                   */
+  SRGD_E_DEVICE = -2,   /* no CUDA device, or device is not sm_100                */
+  SRGD_E_CUDA = -3,     /* a CUDA runtime/driver call failed (see last_error)     */
+  SRGD_E_WORKSPACE = -4 /* workspace too small                                    */
+};
+
+typedef void* srgd_stream_t;
+
+int srgd_version(void);
+const char* srgd_last_error(void);
+/* 0 if `device` is a usable sm_100 GPU, else SRGD_E_DEVICE. */
+int srgd_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler (model.py:3122-3188).  Scalars are the fp32 values of model.py:3127-3134, computed by
+ * the host exactly like the reference (0-dim fp32 tensor math) and passed by value.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct srgd_step_scalars {
+  float alpha;          /* sqrt(sigmoid(log_snr))                         model.py:3131,3134 */
+  float sigma;          /* sqrt(sigmoid(-log_snr))                        model.py:3132,3134 */
+  float alpha_next;     /* sqrt(sigmoid(log_snr_next))                                        */
+  float c;              /* -expm1(log_snr - log_snr_next)                 model.py:3129      */
+  float noise_scale;    /* sqrt(sigmoid(-log_snr_next) * c); 0 on the last step (3168,3184)  */
+  float guidance_scale; /* s in  eps = null + s (cond - null)             model.py:3150,3154 */
+  int32_t clip;         /* clip_sample_denoised                           model.py:3162      */
+} srgd_step_scalars;
+
+/* Fused CFG combine + x0 + clamp + posterior mean + noise add (model.py:3150/3154, 3160-3168,
+ * 3187-3188) over n fp32 elements.  eps_null, noise and x_start may be NULL.  img_next may alias x. */
+int srgd_sampler_step(const float* x, const float* eps_cond, const float* eps_null,
+                      const float* noise, float* img_next, float* x_start, int64_t n,
+                      const srgd_step_scalars* s, srgd_stream_t stream);
+
+/* q_sample (model.py:3434-3447): out = x_start*alpha + noise*sigma.  x_start may be NULL (zeros). */
+int srgd_q_sample(const float* x_start, const float* noise, float* out, int64_t n, float alpha,
+                  float sigma, srgd_stream_t stream);
+
+/* final clamp(-1,1) and (x+1)/2 (model.py:3237-3238, 3404-3405). out may alias img. */
+int srgd_finalize_image(const float* img, float* out, int64_t n, srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM on tcgen05 tensor cores (nn.Conv2d call sites model.py:246, 271,
+ * 300, 303, 341, 342, 109, 78, 647, 668, 583).  D[M=B*Ho*Wo, N=Cout] = sum over taps and input
+ * channel blocks of A(pixel shifted by tap)[M, 64] * W[N, 64]^T, bf16 operands, fp32 TMEM
+ * accumulators.
+ * ------------------------------------------------------------------------------------------ */
+enum { SRGD_CONV_MAX_SRC = 4, SRGD_CONV_MAX_PHASE = 20 };
+
+enum {                     /* srgd_conv_desc.out_mode */
+  SRGD_OUT_BF16_NHWC = 0,  /* out[b][y][x][n]                                                 */
+  SRGD_OUT_PIXEL_SHUFFLE = 1 /* PixelShuffle(2) of the result (model.py:83): weights are packed
+                                so that n = (i*2+j)*C' + c'; out[b][2y+i][2x+j][c'], C' = Cout/4 */
+};
+
+typedef struct srgd_conv_src {
+  const void* ptr;         /* bf16, element (b,y,x,c) at ((b*sb + y*sy + x*sx) + c) elements   */
+  int64_t sb, sy, sx;      /* element strides (multiples of 8)                                 */
+  int32_t H, W, C;         /* extents seen by the kernel (C multiple of 64)                    */
+} srgd_conv_src;
+
+typedef struct srgd_conv_phase {
+  int32_t src;             /* index into srcs[]                                                */
+  int32_t dy, dx;          /* input pixel = output pixel + (dy,dx); out of range reads zero    */
+  int32_t k_start;         /* first weight column (multiple of 64); covers srcs[src].C columns */
+} srgd_conv_phase;
+
+typedef struct srgd_conv_desc {
+  int32_t B, Ho, Wo, Cout; /* Cout multiple of 64                                              */
+  int32_t n_src, n_phase;
+  srgd_conv_src srcs[SRGD_CONV_MAX_SRC];
+  srgd_conv_phase phases[SRGD_CONV_MAX_PHASE];
+  const void* weight;      /* bf16 [Cout][Ktot], K-major                                       */
+  int64_t Ktot;
+  const float* bias;       /* [Cout] or NULL                                                   */
+  const float* row_scale;  /* per output pixel [B*Ho*Wo] fp32 or NULL: acc *= row_scale before bias
+                              (RMSNorm folded into the following 1x1 conv, model.py:207,310,347) */
+  const void* residual;    /* bf16, same layout as out, added last; or NULL                    */
+  int32_t act;             /* 0 none, 1 SiLU (applied after bias, before residual)             */
+  int32_t out_mode;
+  void* out;               /* bf16                                                             */
+  float* gn_partials;      /* NULL, or fp32 [m_tiles*4][8][2]: per (M-tile, epilogue warp) sum and
+                              sum of squares per GroupNorm group of the fp32 result (model.py:247) */
+} srgd_conv_desc;
+
+/* Number of 128-pixel M tiles the kernel will use for (B,Ho,Wo) -- sizes gn_partials. */
+int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo);
+int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream);
+/* Same contract on CUDA cores, one thread per output element.  Debug/verification path used by
+ * the GPU tests to cross-check the tensor-core kernel; never selected by the product path. */
+int srgd_conv_direct(const srgd_conv_desc* d, srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm(8 groups, eps 1e-5) + (scale+1, shift) + SiLU (+ residual)   model.py:247-258, 285
+ * ------------------------------------------------------------------------------------------ */
+/* Reduce the conv epilogue partials to mean / rstd per (sample, group): stats[B][8][2]. */
+int srgd_groupnorm_finalize(const float* gn_partials, float* stats, int32_t B, int32_t H, int32_t W,
+                            int32_t C, srgd_stream_t stream);
+/* Stand-alone statistics pass over a bf16 NHWC tensor (used when the producer was not a conv). */
+int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int32_t H, int32_t W, int32_t C,
+                         srgd_stream_t stream);
+/* y = SiLU( (GN(x)*gamma+beta) * (scale+1) + shift ) [+ residual].  scale_shift: fp32, row b at
+ * scale_shift + b*ss_stride holds [scale(C) | shift(C)] (model.py:279), or NULL.  Row b of the
+ * output reads sample (b % Bx) of x and stats (CFG halves sharing one conv result).  y may alias
+ * x when Bx == B. */
+int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
+                         const float* beta, const float* scale_shift, int64_t ss_stride,
+                         const void* residual, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                         srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RMSNorm pieces (model.py:201-207)
+ * ------------------------------------------------------------------------------------------ */
+/* inv[m] = 1 / max(||x[m,:]||_2, 1e-12) for each of M pixels of a bf16 [M][C] tensor. */
+int srgd_pixel_inv_norm(const void* x, float* inv, int64_t M, int32_t C, srgd_stream_t stream);
+/* y = x / max(||x||,1e-12) * g * sqrt(C) [+ residual]   (to_out.1 + caller's "+ x", 304, 703) */
+int srgd_rmsnorm_residual(const void* x, const float* g, const void* residual, void* y, int64_t M,
+                          int32_t C, srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention cores on the packed qkv tensor bf16 [B][N][3*heads*32] (q | k | v, head-major)
+ * ------------------------------------------------------------------------------------------ */
+/* LinearAttention core, model.py:315-323: softmax(q) over d, softmax(k) over N, ctx = k v^T,
+ * out = ctx^T q * 32^-1/2 -> bf16 [B][N][heads*32].  workspace: srgd_linear_attention_workspace(). */
+size_t srgd_linear_attention_workspace(int32_t B, int32_t N, int32_t heads);
+int srgd_linear_attention(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,
+                          void* workspace, size_t workspace_bytes, srgd_stream_t stream);
+/* Full attention core (Attend, model.py:352): softmax(q k^T * 32^-1/2) v -> bf16 [B][N][heads*32]. */
+int srgd_attention(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,
+                   srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * U-Net entry and exit (model.py:681-687, 722-725) and embeddings (model.py:223-238, 603-619, 264-267)
+ * ------------------------------------------------------------------------------------------ */
+/* cat(x, cond) fp32 NCHW -> bf16 [B][H][W][64] rows for the 7x7 init conv: channel (dx*6+c) holds
+ * input channel c at horizontal offset dx-3 (zero outside), channels 42..63 zero.  Row b reads
+ * x[b % Bx]; cond likewise for rows b < n_cond_rows, zeros for the rest or if cond is NULL
+ * (x_self_cond=None, model.py:682). */
+int srgd_pack_input(const float* x, const float* cond, int32_t n_cond_rows, int32_t Bx, void* out,
+                    int32_t B, int32_t H, int32_t W, srgd_stream_t stream);
+/* eps[b][o][y][x] = bias[o] + sum_c w[o][c] * h[b][y][x][c]   (final_conv, 128 -> 3, fp32 NCHW out) */
+int srgd_final_conv(const void* h, const float* w, const float* bias, float* eps, int32_t B,
+                    int32_t H, int32_t W, int32_t C, int32_t Cout, srgd_stream_t stream);
+/* Generic small dense layer on fp32 rows: y[m][n] = bias[n] + sum_k act_in(x[m][k]) * w[n][k],
+ * act_in: 0 none, 1 SiLU, 2 GELU(erf).  accumulate!=0 adds into y. */
+int srgd_dense_rows(const float* x, const float* w, const float* bias, float* y, int32_t M,
+                    int32_t N, int32_t K, int32_t act_in, int32_t accumulate, srgd_stream_t stream);
+/* [log_snr, sin(2 pi w log_snr), cos(...)]  (model.py:233-238): out fp32 [B][2*half+1]. */
+int srgd_fourier_features(const float* log_snr, const float* weights, float* out, int32_t B,
+                          int32_t half_dim, srgd_stream_t stream);
+/* t[b][:] += table[labels[b]][:] for labels[b] >= 0   (t = t + class_mlp(label), model.py:692-694) */
+int srgd_add_class_rows(float* t, const float* table, const int32_t* labels_dev, int32_t B,
+                        int32_t dim, int32_t num_classes, srgd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole U-Net (ConditionalSRUnet.forward, model.py:678-725) over a packed parameter list.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct srgd_unet_config {
+  int32_t dim;             /* 128 */
+  int32_t n_stages;        /* len(dim_mults), <= 6 */
+  int32_t dim_mults[6];
+  int32_t full_attn[6];
+  int32_t heads, dim_head; /* 4, 32 (dim_head must be 32) */
+  int32_t groups;          /* 8 */
+  int32_t channels;        /* 3 */
+  int32_t sinu_dim;        /* learned_sinusoidal_dim (32) */
+  int32_t num_classes;     /* 3, or 0 for none */
+} srgd_unet_config;
+
+typedef struct srgd_unet srgd_unet;
+
+/* Number of device pointers srgd_unet_create expects for this config, and the name of the i-th one
+ * (the packing contract; srgd_b200/weights.py produces exactly this list from the checkpoint). */
+int srgd_unet_param_count(const srgd_unet_config* cfg);
+const char* srgd_unet_param_name(const srgd_unet_config* cfg, int index);
+int srgd_unet_create(const srgd_unet_config* cfg, const void* const* params_dev, int n_params,
+                     srgd_unet** out);
+void srgd_unet_destroy(srgd_unet* u);
+size_t srgd_unet_workspace_bytes(const srgd_unet* u, int32_t B, int32_t H, int32_t W);
+/* eps[B][3][H][W] = unet(x[b % Bx], log_snr[b], label[b], cond[b % Bx] for b < n_cond_rows).
+ * The classifier-free-guidance 2x batch (model.py:3148-3154) is B = 2*Bx rows: rows [0,Bx) are the
+ * conditional pass, rows [Bx,2Bx) the null pass (labels -1, or n_cond_rows = Bx).
+ * labels_dev: int32 [B] device, entries < 0 select the null label (class_label=None, model.py:692);
+ * NULL = all null.  cond_dev may be NULL (all zeros, model.py:682).
+ * conv_impl: 0 = tcgen05 implicit GEMM (product path), 1 = CUDA-core direct (debug). */
+int srgd_unet_forward(srgd_unet* u, const float* x_dev, const float* cond_dev,
+                      const float* log_snr_dev, const int32_t* labels_dev, int32_t n_cond_rows,
+                      int32_t Bx, float* eps_dev, int32_t B, int32_t H, int32_t W,
+                      void* workspace_dev, size_t workspace_bytes, int32_t conv_impl,
+                      srgd_stream_t stream);
+/* Debug taps: after a forward, copy the named bf16 NHWC activation (e.g. "downs.0.0") into
+ * out_dev; returns its element count through *n, or SRGD_E_ARG if unknown.  Enabled per forward
+ * with srgd_unet_set_tap(name) before the call (one tap at a time; NULL disables). */
+int srgd_unet_set_tap(srgd_unet* u, const char* name, void* out_dev, size_t out_bytes);
+/* Kernels launched by the last srgd_unet_forward on this handle. */
+int srgd_unet_last_launch_count(const srgd_unet* u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGD_B200_H */

@@ -1,0 +1,144 @@
+"""Command-line super-resolution with the srgd_b200 CUDA path.
+
+Same flags, defaults, file handling and output naming as the reference CLI (reference:
+inference.py:21-44 flags, 47-56 seeding, 59-98 per-image pipeline, 108-142 directory loop), so
+`python inference.py -c <yaml> -m <ckpt> --class_cond_scale F --test_label I --seed I --input_dir D
+--output_dir D` is a drop-in.  Differences: the model runs on an sm_100 GPU only (explicit error
+otherwise) and `--world_size/--rank` (or torchrun's env) shard the sorted file list across GPUs,
+the multi-GPU analogue of the reference's manual --start_index/--end_index split.
+"""
+import glob
+import logging
+import os
+import random
+from argparse import ArgumentParser
+
+import numpy as np
+import torch
+from PIL import Image
+
+from config import load_config
+from model import get_model
+
+logger = logging.getLogger("srgd_b200")
+
+
+def parse_args(argv=None):
+    ap = ArgumentParser(description="Real-SRGD x4 super-resolution (B200-native sampling path)")
+    ap.add_argument('-c', '--conf', required=True, help='Path to config file')
+    ap.add_argument('-m', '--ckpt_path', type=str, required=True)
+    ap.add_argument('--input_dir', type=str, required=True)
+    ap.add_argument('--output_dir', type=str, required=True)
+    for name, typ, default in (('batch_size', int, 8), ('num_sample_steps', int, 250), ('interpolation', str, 'bicubic'),
+                               ('cond_scale', float, 1.0), ('class_cond_scale', float, 1.0),
+                               ('guidance_start_steps', int, 0), ('class_guidance_start_steps', int, 0),
+                               ('generation_start_steps', int, 0), ('start_index', int, 0), ('end_index', int, None),
+                               ('test_label', int, None), ('seed', int, 71), ('backend', str, 'ddp')):
+        ap.add_argument('--' + name, type=typ, default=default)
+    ap.add_argument('--no_amp', dest='amp', action='store_false')
+    ap.add_argument('--no_dpmpp_solver', dest='use_dpmpp_solver', action='store_false')
+    # multi-GPU sharding of the file list (defaults come from torchrun's environment)
+    ap.add_argument('--world_size', type=int, default=int(os.environ.get('WORLD_SIZE', 1)))
+    ap.add_argument('--rank', type=int, default=int(os.environ.get('RANK', 0)))
+    return ap.parse_args(argv)
+
+
+def seed_everything(seed):
+    """Per-image reseed of every generator the sampling loop draws from (inference.py:47-56)."""
+    random.seed(seed)
+    os.environ['PYTHONHASHSEED'] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+
+
+def _to_unit_tensor(image: Image.Image) -> torch.Tensor:
+    """PIL RGB -> float [1,3,H,W] in [0,1] (what torchvision's ToTensor does for uint8 images)."""
+    arr = np.asarray(image, dtype=np.uint8)
+    return torch.from_numpy(arr).permute(2, 0, 1).unsqueeze(0).float().div(255.)
+
+
+def _to_image(t: torch.Tensor) -> Image.Image:
+    """float [3,H,W] in [0,1] -> PIL RGB with ToPILImage's mul(255).byte() truncation (inference.py:94)."""
+    arr = t.detach().mul(255).byte().permute(1, 2, 0).cpu().numpy()
+    return Image.fromarray(arr, mode='RGB')
+
+
+def sr_target_image(image, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
+                    class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
+                    num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71):
+    width, height = image.size
+    # the reference maps both 'bicubic' and 'lanczos' to bicubic (inference.py:66-69)
+    upscaled = image.resize((width * scale, height * scale), resample=Image.BICUBIC)
+    condition_x = _to_unit_tensor(upscaled).to(sr_model.device)
+    label = None if test_label is None else torch.tensor([test_label], dtype=torch.long, device=sr_model.device)
+    seed_everything(seed)
+    with torch.inference_mode():
+        output = sr_model.tiled_sample(batch_size=batch_size, condition_x=condition_x, class_label=label,
+                                       cond_scale=cond_scale, guidance_start_steps=guidance_start_steps,
+                                       class_cond_scale=class_cond_scale,
+                                       class_guidance_start_steps=class_guidance_start_steps,
+                                       generation_start_steps=generation_start_steps,
+                                       num_sample_steps=num_sample_steps, amp=enable_amp)
+    sr_img = _to_image(output[0])
+    assert sr_img.size == (width * 4, height * 4)
+    return sr_img
+
+
+def try_open_image(image_path):
+    try:
+        return Image.open(image_path).convert('RGB')
+    except (IOError, SyntaxError):
+        return None
+
+
+def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0,
+                           guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                           generation_start_steps=0, num_sample_steps=250, start_index=0, end_index=None,
+                           enable_amp=False, interpolation='bicubic', seed=71, world_size=1, rank=0):
+    print(f"save images at: {output_dir}")
+    os.makedirs(output_dir, exist_ok=True)
+    files = sorted(glob.glob(f"{input_dir}/*"))[start_index:end_index][rank::world_size]
+    for path in files:
+        save_path = os.path.join(output_dir, os.path.basename(path).replace('.png', '_out.png'))
+        if os.path.exists(save_path):           # doubles as resume-after-crash (inference.py:126)
+            print('skip')
+            continue
+        image = try_open_image(path)
+        if image is None:
+            print('Invalid image or unable to open image:', path)
+            continue
+        sr_target_image(image, sr_model, scale=scale, batch_size=batch_size, test_label=test_label,
+                        cond_scale=cond_scale, guidance_start_steps=guidance_start_steps,
+                        class_cond_scale=class_cond_scale, class_guidance_start_steps=class_guidance_start_steps,
+                        generation_start_steps=generation_start_steps, num_sample_steps=num_sample_steps,
+                        enable_amp=enable_amp, interpolation=interpolation, seed=seed).save(save_path)
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    conf = load_config(args.conf)
+    conf.num_sample_steps = args.num_sample_steps
+    conf.ckpt_path = args.ckpt_path
+    if not torch.cuda.is_available():
+        raise RuntimeError("srgd_b200 needs an sm_100 (B200) CUDA device; there is no CPU fallback. "
+                           "Use the reference implementation for CPU inference.")
+    local_rank = int(os.environ.get('LOCAL_RANK', args.rank % max(1, torch.cuda.device_count())))
+    torch.cuda.set_device(local_rank)
+    ema_model = get_model(conf, logger)
+    sr_model = ema_model.module.eval().to(torch.device('cuda', local_rank))
+    print(args)
+    batch_sr_target_images(args.input_dir, args.output_dir, sr_model, scale=4, batch_size=args.batch_size,
+                           test_label=args.test_label, cond_scale=args.cond_scale,
+                           guidance_start_steps=args.guidance_start_steps, class_cond_scale=args.class_cond_scale,
+                           class_guidance_start_steps=args.class_guidance_start_steps,
+                           generation_start_steps=args.generation_start_steps,
+                           num_sample_steps=args.num_sample_steps, start_index=args.start_index,
+                           end_index=args.end_index, enable_amp=args.amp, interpolation=args.interpolation,
+                           seed=args.seed, world_size=args.world_size, rank=args.rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,109 @@
+// Shared helpers for the srgd_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/srgd_b200.h"
+
+namespace srgd {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_device();                       // SRGD_OK if current device is sm_100, cached
+int fail_cuda(cudaError_t e, const char* what);
+
+#define SRGD_CUDA_OK(expr)                                         \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return ::srgd::fail_cuda(_e, #expr);    \
+  } while (0)
+
+#define SRGD_REQUIRE(cond, ...)                                    \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      ::srgd::set_error(__VA_ARGS__);                              \
+      return SRGD_E_ARG;                                           \
+    }                                                              \
+  } while (0)
+
+#define SRGD_LAUNCH_OK(what)                                       \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return ::srgd::fail_cuda(_e, what);     \
+  } while (0)
+
+static inline cudaStream_t as_stream(srgd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+
+// launch counter (gpu_launches in bench.py / srgd_unet_last_launch_count)
+extern thread_local long g_launches;
+static inline void count_launch(int n = 1) { g_launches += n; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+// 8 bf16 <-> 8 floats through one 16-byte vector
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+// streaming 16-byte accesses (activations are touched once per kernel: keep them out of L1)
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#endif  // __CUDACC__
+}  // namespace srgd

@@ -1,0 +1,519 @@
+// Convolution as implicit GEMM on the Blackwell 5th-gen tensor cores (tcgen05.mma, TMEM
+// accumulators, TMA operand staging).  Replaces every nn.Conv2d on the reference hot path:
+// conv3x3 (model.py:246, 647, 668), conv1x1 (271, 300, 303, 341, 342), Downsample's
+// space-to-depth + 1x1 (106-110), PixelShuffleUpsample's 1x1 + SiLU + PixelShuffle (70-98) and the
+// 7x7 init conv (583) after srgd_pack_input.
+//
+// GEMM view:  D[M = B*Ho*Wo pixels, N = Cout] = sum_phases A_phase[M, C_src] * W[N, k_phase..]^T.
+// A "phase" is one filter tap of one source tensor: the A tile of a phase is the NHWC activation
+// patch of the CTA's 128 output pixels shifted by (dy,dx); TMA's tiled mode fetches it as a 4-D box
+// {64 ch, TW, TH, TN} whose out-of-range pixels are zero-filled (= conv zero padding), directly in
+// the 128-byte-swizzled K-major layout tcgen05.mma consumes.  A channel concat (model.py:713-722)
+// is just more phases reading a second source: the cat is never materialised.
+//
+// Kernel organisation (persistent, one CTA per SM, 256 threads):
+//   warp 0 lane 0 : TMA producer  (STAGES-deep smem ring, full/empty mbarriers)
+//   warp 1 lane 0 : MMA issuer    (4 x tcgen05.mma K=16 per 64-wide k-block; commit -> empty barrier)
+//   warp 2        : TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4..7    : epilogue      (tcgen05.ld 32x32b, row_scale, bias, GroupNorm partial sums, SiLU,
+//                                  residual, bf16 store in NHWC or pixel-shuffled NHWC)
+// The double-buffered accumulator lets the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tiles.h"
+
+namespace srgd {
+
+constexpr int kBM = 128;          // output pixels per tile (UMMA M)
+constexpr int kBK = 64;           // bf16 channels per k-block (one 128-byte swizzle row)
+constexpr int kThreads = 256;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KiB
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap a_maps[SRGD_CONV_MAX_SRC];
+  CUtensorMap w_map;
+  int32_t n_src;
+  int32_t n_phase;
+  int32_t total_kblocks;
+  int8_t ph_src[SRGD_CONV_MAX_PHASE];
+  int8_t ph_dy[SRGD_CONV_MAX_PHASE];
+  int8_t ph_dx[SRGD_CONV_MAX_PHASE];
+  int16_t ph_cblocks[SRGD_CONV_MAX_PHASE];
+  int32_t ph_kblk[SRGD_CONV_MAX_PHASE];
+  int32_t B, Ho, Wo, Cout;
+  int32_t tw_log2, th_log2;       // tile = TN x TH x TW pixels, TN*TH*TW = 128
+  int32_t tiles_x, tiles_y, tiles_b;
+  int32_t m_tiles, n_tiles, total_tiles;
+  int32_t group_size;             // Cout / 8 (GroupNorm group width in channels)
+  int32_t act, out_mode;
+  const float* bias;
+  const float* row_scale;
+  const bf16* residual;
+  bf16* out;
+  float* gn_partials;
+};
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr, gn staging
+  static constexpr int kGnOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kGnBytes = 4 * (BN / 8) * 2 * 4;
+  static constexpr int kTotal = kGnOffset + kGnBytes + 1024;   // +1024: manual 1 KiB alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  using L = ConvSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* gn_smem = reinterpret_cast<float*>(smem + L::kGnOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BN;                 // 128 / 256 / 512: powers of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_src; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
+    ptx::prefetch_tmap(&p.w_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);                 // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+  const int tn_log2 = 7 - p.tw_log2 - p.th_log2;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int tb = m_tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, b0 = tb << tn_log2;
+      for (int ph = 0; ph < p.n_phase; ++ph) {
+        const CUtensorMap* amap = &p.a_maps[p.ph_src[ph]];
+        const int xs = x0 + p.ph_dx[ph], ys = y0 + p.ph_dy[ph];
+        const int kblk0 = p.ph_kblk[ph];
+        const int ncb = p.ph_cblocks[ph];
+        for (int cb = 0; cb < ncb; ++cb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::kStageBytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::tma_load_4d(a_dst, amap, &full_bar[stage], cb * kBK, xs, ys, b0);
+          ptx::tma_load_2d(b_dst, &p.w_map, &full_bar[stage], (kblk0 + cb) * kBK, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.total_kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(smem + stage * L::kStageBytes);
+        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr);
+        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
+        if (kb == p.total_kblocks - 1) ptx::umma_commit(&tfull_bar[acc]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                         // tile row == output pixel slot
+    const int w_i = r & (tw - 1);
+    const int h_i = (r >> p.tw_log2) & (th - 1);
+    const int n_i = r >> (p.tw_log2 + p.th_log2);
+    float* gn_w = gn_smem + q * (BN / 8) * 2;            // this warp's staging row: [BN/8][2]
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int tb = m_tile / (p.tiles_x * p.tiles_y);
+      const int x = (tx << p.tw_log2) + w_i;
+      const int y = (ty << p.th_log2) + h_i;
+      const int b = (tb << tn_log2) + n_i;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+      const int n0 = n_tile * BN;
+      const float rs = (p.row_scale != nullptr && valid) ? p.row_scale[pix] : 1.0f;
+
+      if (p.gn_partials != nullptr) {
+        for (int i = lane; i < (BN / 8) * 2; i += 32) gn_w[i] = 0.f;
+        __syncwarp();
+      }
+
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_row + c * 32, v);
+        ptx::tmem_ld_wait();
+        const int nc = n0 + c * 32;                      // first output channel of this chunk
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + j));
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        }
+        if (p.gn_partials != nullptr) {
+          // per 8-channel sub-block sums over this warp's 32 pixels (masked rows contribute 0)
+          float s8[4], q8[4];
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) {
+            float s = 0.f, qq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = valid ? f[sb * 8 + j] : 0.f;
+              s += t;
+              qq += t * t;
+            }
+            s8[sb] = s;
+            q8[sb] = qq;
+          }
+          if (p.group_size >= 32) {                      // whole chunk lies in one group
+            float s = warp_sum(s8[0] + s8[1] + s8[2] + s8[3]);
+            float qq = warp_sum(q8[0] + q8[1] + q8[2] + q8[3]);
+            if (lane == 0) {
+              const int g = (c * 32) / p.group_size;     // group index local to this tile
+              gn_w[g * 2] += s;
+              gn_w[g * 2 + 1] += qq;
+            }
+          } else {
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb) {
+              float s = warp_sum(s8[sb]);
+              float qq = warp_sum(q8[sb]);
+              if (lane == 0) {
+                const int g = (c * 32 + sb * 8) / p.group_size;
+                gn_w[g * 2] += s;
+                gn_w[g * 2 + 1] += qq;
+              }
+            }
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+        }
+        if (valid && nc < p.Cout) {
+          int64_t off;
+          if (p.out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
+            const int cq = p.Cout >> 2;                  // C' output channels
+            const int sub = nc / cq;                     // (i*2 + j) sub-pixel
+            const int cc = nc - sub * cq;
+            off = (((int64_t)b * (2 * p.Ho) + (2 * y + (sub >> 1))) * (2 * p.Wo) + (2 * x + (sub & 1))) * cq + cc;
+          } else {
+            off = pix * p.Cout + nc;
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float rr[8];
+              unpack8(ld_stream(p.residual + off + j), rr);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) f[j + t] += rr[t];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st_stream(p.out + off + j, pack8(f + j));
+        }
+      }
+      // accumulator fully read: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if (p.gn_partials != nullptr) {
+        __syncwarp();
+        const int groups_in_tile = BN / p.group_size;
+        const int g0 = n0 / p.group_size;
+        float* dst = p.gn_partials + ((int64_t)(m_tile * 4 + q) * 8) * 2;
+        for (int i = lane; i < groups_in_tile * 2; i += 32) {
+          const int g = g0 + (i >> 1);
+          if (g < 8) dst[g * 2 + (i & 1)] = gn_w[i];
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core direct evaluation of the same descriptor (debug / verification only)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_direct_kernel(srgd_conv_desc d) {
+  const int64_t total = (int64_t)d.B * d.Ho * d.Wo * d.Cout;
+  const bf16* wt = reinterpret_cast<const bf16*>(d.weight);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % d.Cout);
+    const int64_t pix = idx / d.Cout;
+    const int x = (int)(pix % d.Wo);
+    const int y = (int)((pix / d.Wo) % d.Ho);
+    const int b = (int)(pix / ((int64_t)d.Wo * d.Ho));
+    float acc = 0.f;
+    for (int ph = 0; ph < d.n_phase; ++ph) {
+      const srgd_conv_src& s = d.srcs[d.phases[ph].src];
+      const int yy = y + d.phases[ph].dy, xx = x + d.phases[ph].dx;
+      if (yy < 0 || yy >= s.H || xx < 0 || xx >= s.W) continue;
+      const bf16* a = reinterpret_cast<const bf16*>(s.ptr) + (int64_t)b * s.sb + (int64_t)yy * s.sy + (int64_t)xx * s.sx;
+      const bf16* w = wt + (int64_t)n * d.Ktot + d.phases[ph].k_start;
+      for (int c = 0; c < s.C; ++c) acc += __bfloat162float(a[c]) * __bfloat162float(w[c]);
+    }
+    if (d.row_scale) acc *= d.row_scale[pix];
+    if (d.bias) acc += d.bias[n];
+    if (d.act == 1) acc = silu_f(acc);
+    int64_t off;
+    if (d.out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
+      const int cq = d.Cout >> 2, sub = n / cq, cc = n - sub * cq;
+      off = (((int64_t)b * (2 * d.Ho) + (2 * y + (sub >> 1))) * (2 * d.Wo) + (2 * x + (sub & 1))) * cq + cc;
+    } else {
+      off = pix * d.Cout + n;
+    }
+    if (d.residual) acc += __bfloat162float(reinterpret_cast<const bf16*>(d.residual)[off]);
+    reinterpret_cast<bf16*>(d.out)[off] = __float2bfloat16(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int validate_desc(const srgd_conv_desc* d) {
+  SRGD_REQUIRE(d != nullptr, "conv: null descriptor");
+  SRGD_REQUIRE(d->B > 0 && d->Ho > 0 && d->Wo > 0, "conv: bad output extent %dx%dx%d", d->B, d->Ho, d->Wo);
+  SRGD_REQUIRE(d->Cout > 0 && d->Cout % 64 == 0, "conv: Cout=%d must be a positive multiple of 64", d->Cout);
+  SRGD_REQUIRE(d->n_src >= 1 && d->n_src <= SRGD_CONV_MAX_SRC, "conv: n_src=%d out of range", d->n_src);
+  SRGD_REQUIRE(d->n_phase >= 1 && d->n_phase <= SRGD_CONV_MAX_PHASE, "conv: n_phase=%d out of range", d->n_phase);
+  SRGD_REQUIRE(d->weight && d->out, "conv: null weight/out");
+  SRGD_REQUIRE(((uintptr_t)d->weight | (uintptr_t)d->out | (uintptr_t)d->bias | (uintptr_t)d->residual) % 16 == 0,
+               "conv: weight/out/bias/residual must be 16-byte aligned");
+  for (int i = 0; i < d->n_src; ++i) {
+    const srgd_conv_src& s = d->srcs[i];
+    SRGD_REQUIRE(s.ptr && ((uintptr_t)s.ptr % 16) == 0, "conv: src %d pointer null or not 16-byte aligned", i);
+    SRGD_REQUIRE(s.C > 0 && s.C % 64 == 0, "conv: src %d C=%d must be a multiple of 64", i, s.C);
+    SRGD_REQUIRE(s.sx % 8 == 0 && s.sy % 8 == 0 && s.sb % 8 == 0 && s.sx > 0, "conv: src %d strides must be multiples of 8", i);
+    SRGD_REQUIRE(s.H > 0 && s.W > 0, "conv: src %d bad extent", i);
+  }
+  for (int i = 0; i < d->n_phase; ++i) {
+    const srgd_conv_phase& ph = d->phases[i];
+    SRGD_REQUIRE(ph.src >= 0 && ph.src < d->n_src, "conv: phase %d src out of range", i);
+    SRGD_REQUIRE(ph.k_start >= 0 && ph.k_start % 64 == 0 && ph.k_start + d->srcs[ph.src].C <= d->Ktot,
+                 "conv: phase %d weight columns [%d,+%d) outside Ktot=%lld", i, ph.k_start, d->srcs[ph.src].C,
+                 (long long)d->Ktot);
+    SRGD_REQUIRE(ph.dy >= -64 && ph.dy <= 64 && ph.dx >= -64 && ph.dx <= 64, "conv: phase %d tap out of range", i);
+  }
+  SRGD_REQUIRE(d->Ktot % 64 == 0, "conv: Ktot must be a multiple of 64");
+  SRGD_REQUIRE(d->out_mode == SRGD_OUT_BF16_NHWC || d->out_mode == SRGD_OUT_PIXEL_SHUFFLE, "conv: bad out_mode");
+  if (d->out_mode == SRGD_OUT_PIXEL_SHUFFLE)
+    SRGD_REQUIRE(d->Cout % 128 == 0, "conv: pixel-shuffle output needs Cout %% 128 == 0");
+  return SRGD_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
+  using L = ConvSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      L::kTotal));
+    configured = true;
+  }
+  int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
+  conv_igemm_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, st>>>(kp);
+  SRGD_LAUNCH_OK("conv_igemm_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+}  // namespace srgd
+
+using namespace srgd;
+
+extern "C" int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  return tile_geom(B, Ho, Wo).m_tiles;
+}
+
+extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = validate_desc(d);
+  if (rc) return rc;
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) {
+    set_error("conv: cuTensorMapEncodeTiled not available from the driver");
+    return SRGD_E_CUDA;
+  }
+  const TileGeom g = tile_geom(d->B, d->Ho, d->Wo);
+
+  // pick the N tile: widest that divides Cout, but keep enough tiles to fill the SMs
+  int BN = 64;
+  if (d->Cout % 256 == 0 && (int64_t)g.m_tiles * (d->Cout / 256) >= sm_count()) BN = 256;
+  else if (d->Cout % 128 == 0) BN = 128;
+  if (d->gn_partials) {
+    SRGD_REQUIRE(d->Cout % 8 == 0 && (d->Cout / 8) % 8 == 0, "conv: GroupNorm partials need Cout %% 64 == 0");
+    SRGD_REQUIRE(g.tn_log2 <= 2, "conv: GroupNorm partials need H*W >= 32 (got %dx%d)", d->Ho, d->Wo);
+    while (BN < d->Cout / 8) BN *= 2;                    // a tile must hold whole groups
+    SRGD_REQUIRE(BN <= 256 && d->Cout % BN == 0, "conv: cannot tile Cout=%d for GroupNorm partials", d->Cout);
+  }
+
+  ConvKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < d->n_src; ++i) {
+    const srgd_conv_src& s = d->srcs[i];
+    const cuuint64_t gdim[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)d->B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)s.sx * 2, (cuuint64_t)s.sy * 2, (cuuint64_t)s.sb * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, 1u << g.tw_log2, 1u << g.th_log2, 1u << g.tn_log2};
+    CUresult r = encode(&kp.a_maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.ptr), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv: cuTensorMapEncodeTiled(src %d: C=%d W=%d H=%d B=%d sx=%lld sy=%lld sb=%lld) failed with %d", i,
+                s.C, s.W, s.H, d->B, (long long)s.sx, (long long)s.sy, (long long)s.sb, (int)r);
+      return SRGD_E_CUDA;
+    }
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Cout};
+    const cuuint64_t gstr[1] = {(cuuint64_t)d->Ktot * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+    CUresult r = encode(&kp.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv: cuTensorMapEncodeTiled(weight Ktot=%lld Cout=%d) failed with %d", (long long)d->Ktot, d->Cout,
+                (int)r);
+      return SRGD_E_CUDA;
+    }
+  }
+  kp.n_src = d->n_src;
+  kp.n_phase = d->n_phase;
+  int total_kb = 0;
+  for (int i = 0; i < d->n_phase; ++i) {
+    kp.ph_src[i] = (int8_t)d->phases[i].src;
+    kp.ph_dy[i] = (int8_t)d->phases[i].dy;
+    kp.ph_dx[i] = (int8_t)d->phases[i].dx;
+    kp.ph_cblocks[i] = (int16_t)(d->srcs[d->phases[i].src].C / kBK);
+    kp.ph_kblk[i] = d->phases[i].k_start / kBK;
+    total_kb += kp.ph_cblocks[i];
+  }
+  kp.total_kblocks = total_kb;
+  kp.B = d->B; kp.Ho = d->Ho; kp.Wo = d->Wo; kp.Cout = d->Cout;
+  kp.tw_log2 = g.tw_log2; kp.th_log2 = g.th_log2;
+  kp.tiles_x = g.tiles_x; kp.tiles_y = g.tiles_y; kp.tiles_b = g.tiles_b;
+  kp.m_tiles = g.m_tiles;
+  kp.n_tiles = (d->Cout + BN - 1) / BN;
+  kp.total_tiles = kp.m_tiles * kp.n_tiles;
+  kp.group_size = d->Cout / 8;
+  kp.act = d->act; kp.out_mode = d->out_mode;
+  kp.bias = d->bias; kp.row_scale = d->row_scale;
+  kp.residual = reinterpret_cast<const bf16*>(d->residual);
+  kp.out = reinterpret_cast<bf16*>(d->out);
+  kp.gn_partials = d->gn_partials;
+
+  cudaStream_t st = as_stream(stream);
+  switch (BN) {
+    case 64: return launch_igemm<64, 8>(kp, st);
+    case 128: return launch_igemm<128, 6>(kp, st);
+    default: return launch_igemm<256, 4>(kp, st);
+  }
+}
+
+extern "C" int srgd_conv_direct(const srgd_conv_desc* d, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = validate_desc(d);
+  if (rc) return rc;
+  SRGD_REQUIRE(d->gn_partials == nullptr, "conv_direct: GroupNorm partials are only produced by srgd_conv_igemm");
+  const int64_t total = (int64_t)d->B * d->Ho * d->Wo * d->Cout;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 32) blocks = (int64_t)sm_count() * 32;
+  conv_direct_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(*d);
+  SRGD_LAUNCH_OK("conv_direct_kernel");
+  count_launch();
+  return SRGD_OK;
+}

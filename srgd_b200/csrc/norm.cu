@@ -1,0 +1,319 @@
+// GroupNorm + scale/shift + SiLU (+ residual) and RMSNorm kernels on bf16 NHWC activations.
+// Reference: Block.forward model.py:250-259 (nn.GroupNorm(8, C), eps 1e-5, affine), ResnetBlock's
+// `h + res_conv(x)` (model.py:285), RMSNorm model.py:201-207.
+//
+// All of these are HBM-bound streaming passes: 16-byte vector accesses (8 bf16 channels), fp32
+// math, per-(sample, channel) affine folded into one FMA:  y = silu(x * A[c] + B[c]) with
+//   A = rstd*gamma*(scale+1),  B = (beta - mean*rstd*gamma)*(scale+1) + shift.
+// Algorithmic bytes: 2 B read + 2 B written per element (+2 B when a residual is added).
+#include "common.cuh"
+#include "tiles.h"
+
+namespace srgd {
+
+constexpr float kGnEps = 1e-5f;        // nn.GroupNorm default (model.py:247)
+constexpr int kGroups = 8;
+
+// ---- statistics ------------------------------------------------------------------------------
+// One block per (sample, group): fold the conv-epilogue partial sums (conv_igemm.cu) in fp64.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partials,
+                                                          float* __restrict__ stats, int H, int W, int C,
+                                                          TileGeom g) {
+  const int n = blockIdx.x / kGroups, grp = blockIdx.x % kGroups;
+  const int tb = n >> g.tn_log2, n_i = n & ((1 << g.tn_log2) - 1);
+  const int tiles_per_b = g.tiles_x * g.tiles_y;
+  const int warps_per_sample = 4 >> g.tn_log2;           // tn_log2 <= 2 (checked by the conv launcher)
+  const int first_warp = n_i * warps_per_sample;
+  const int entries = tiles_per_b * warps_per_sample;
+  double s = 0.0, q = 0.0;
+  for (int e = threadIdx.x; e < entries; e += blockDim.x) {
+    const int t = e / warps_per_sample, w = e % warps_per_sample;
+    const float* p = partials + ((int64_t)((tb * tiles_per_b + t) * 4 + first_warp + w) * kGroups + grp) * 2;
+    s += (double)p[0];
+    q += (double)p[1];
+  }
+  __shared__ double sh[2][4];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+    q = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    const double cnt = (double)H * W * (C / kGroups);
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;                  // biased variance, as nn.GroupNorm
+    if (var < 0.0) var = 0.0;
+    stats[(n * kGroups + grp) * 2] = (float)mean;
+    stats[(n * kGroups + grp) * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+  }
+}
+
+// Stand-alone statistics over a bf16 NHWC tensor: one block per (sample, group).
+__global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats,
+                                                       int HW, int C) {
+  const int n = blockIdx.x / kGroups, grp = blockIdx.x % kGroups;
+  const int G = C / kGroups;                             // multiple of 8
+  const int vec_per_pix = G / 8;
+  const int64_t total = (int64_t)HW * vec_per_pix;
+  const bf16* base = x + (int64_t)n * HW * C + grp * G;
+  float s = 0.f, q = 0.f;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t pix = i / vec_per_pix;
+    const int v = (int)(i % vec_per_pix);
+    float f[8];
+    unpack8(ld_stream(base + pix * C + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += f[j]; q += f[j] * f[j]; }
+  }
+  __shared__ double sh[2][16];
+  double ds = warp_sum(s), dq = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ds; sh[1][threadIdx.x >> 5] = dq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ds = 0; dq = 0;
+    for (int i = 0; i < 16; ++i) { ds += sh[0][i]; dq += sh[1][i]; }
+    const double cnt = (double)HW * G;
+    const double mean = ds / cnt;
+    double var = dq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(n * kGroups + grp) * 2] = (float)mean;
+    stats[(n * kGroups + grp) * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+  }
+}
+
+// ---- apply -----------------------------------------------------------------------------------
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta,
+                                                       const float* __restrict__ scale_shift, int64_t ss_stride,
+                                                       const bf16* residual, bf16* y, int HW, int C) {
+  extern __shared__ float sm[];                          // A[C] | B[C]
+  float* sA = sm;
+  float* sB = sm + C;
+  const int b = blockIdx.y;
+  const int bs = b % Bx;
+  const int G = C / kGroups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = stats[(bs * kGroups + c / G) * 2];
+    const float rstd = stats[(bs * kGroups + c / G) * 2 + 1];
+    float a = rstd * gamma[c];
+    float bb = beta[c] - mean * a;
+    if (scale_shift != nullptr) {
+      const float sc = scale_shift[(int64_t)b * ss_stride + c] + 1.0f;     // model.py:256
+      const float sh = scale_shift[(int64_t)b * ss_stride + C + c];
+      a *= sc;
+      bb = bb * sc + sh;
+    }
+    sA[c] = a;
+    sB[c] = bb;
+  }
+  __syncthreads();
+  const int vec_per_pix = C / 8;
+  const int64_t total = (int64_t)HW * vec_per_pix;
+  const bf16* xs = x + (int64_t)bs * HW * C;
+  const bf16* rs = HAS_RES ? residual + (int64_t)b * HW * C : nullptr;
+  bf16* ys = y + (int64_t)b * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vec_per_pix) * 8;
+    float f[8];
+    unpack8(ld_stream(xs + i * 8), f);
+    const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
+    f[0] = silu_f(fmaf(f[0], a0.x, b0.x)); f[1] = silu_f(fmaf(f[1], a0.y, b0.y));
+    f[2] = silu_f(fmaf(f[2], a0.z, b0.z)); f[3] = silu_f(fmaf(f[3], a0.w, b0.w));
+    f[4] = silu_f(fmaf(f[4], a1.x, b1.x)); f[5] = silu_f(fmaf(f[5], a1.y, b1.y));
+    f[6] = silu_f(fmaf(f[6], a1.z, b1.z)); f[7] = silu_f(fmaf(f[7], a1.w, b1.w));
+    if (HAS_RES) {
+      float r[8];
+      unpack8(ld_stream(rs + i * 8), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    st_stream(ys + i * 8, pack8(f));
+  }
+}
+
+// ---- RMSNorm ---------------------------------------------------------------------------------
+// LP lanes cooperate on one pixel (LP = min(32, C/8)); each lane keeps its share of the row in
+// registers (<= 4 vectors of 8 channels: C <= 1024).
+template <int LP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LP>
+__global__ void __launch_bounds__(256) pixel_inv_norm_kernel(const bf16* __restrict__ x, float* __restrict__ inv,
+                                                             int64_t M, int C) {
+  const int vec_per_pix = C / 8;
+  const int sub = threadIdx.x % LP;
+  const int64_t pix_per_block = blockDim.x / LP;
+  for (int64_t m = (int64_t)blockIdx.x * pix_per_block + threadIdx.x / LP; m < M;
+       m += (int64_t)gridDim.x * pix_per_block) {
+    float ss = 0.f;
+    for (int v = sub; v < vec_per_pix; v += LP) {
+      float f[8];
+      unpack8(ld_stream(x + m * C + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    ss = group_sum<LP>(ss);
+    if (sub == 0) inv[m] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                 // F.normalize eps (model.py:207)
+  }
+}
+
+template <int LP, bool HAS_RES>
+__global__ void __launch_bounds__(256) rmsnorm_residual_kernel(const bf16* x, const float* __restrict__ g,
+                                                               const bf16* residual, bf16* y, int64_t M, int C,
+                                                               float sqrt_c) {
+  const int vec_per_pix = C / 8;
+  const int sub = threadIdx.x % LP;
+  const int64_t pix_per_block = blockDim.x / LP;
+  for (int64_t m = (int64_t)blockIdx.x * pix_per_block + threadIdx.x / LP; m < M;
+       m += (int64_t)gridDim.x * pix_per_block) {
+    float f[4][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int v = sub + t * LP;
+      if (v < vec_per_pix) {
+        unpack8(ld_stream(x + m * C + v * 8), f[t]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += f[t][j] * f[t][j];
+      }
+    }
+    ss = group_sum<LP>(ss);
+    const float scale = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int v = sub + t * LP;
+      if (v < vec_per_pix) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + v * 8 + 4));
+        float o[8] = {f[t][0] * scale * g0.x, f[t][1] * scale * g0.y, f[t][2] * scale * g0.z, f[t][3] * scale * g0.w,
+                      f[t][4] * scale * g1.x, f[t][5] * scale * g1.y, f[t][6] * scale * g1.z, f[t][7] * scale * g1.w};
+        if (HAS_RES) {
+          float r[8];
+          unpack8(ld_stream(residual + m * C + v * 8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        st_stream(y + m * C + v * 8, pack8(o));
+      }
+    }
+  }
+}
+
+static int stream_grid(int64_t items_per_block_total, int ctas_per_sm) {
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (items_per_block_total < 1) items_per_block_total = 1;
+  return (int)(items_per_block_total < cap ? items_per_block_total : cap);
+}
+
+}  // namespace srgd
+
+using namespace srgd;
+
+extern "C" int srgd_groupnorm_finalize(const float* gn_partials, float* stats, int32_t B, int32_t H, int32_t W,
+                                       int32_t C, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(gn_partials && stats && B > 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0,
+               "groupnorm_finalize: bad arguments");
+  const TileGeom g = tile_geom(B, H, W);
+  SRGD_REQUIRE(g.tn_log2 <= 2, "groupnorm_finalize: needs H*W >= 32");
+  gn_finalize_kernel<<<B * kGroups, 128, 0, as_stream(stream)>>>(gn_partials, stats, H, W, C, g);
+  SRGD_LAUNCH_OK("gn_finalize_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int32_t H, int32_t W, int32_t C,
+                                    srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && stats && B > 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0, "groupnorm_stats: bad arguments");
+  gn_stats_kernel<<<B * kGroups, 512, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(x), stats, H * W, C);
+  SRGD_LAUNCH_OK("gn_stats_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
+                                    const float* beta, const float* scale_shift, int64_t ss_stride,
+                                    const void* residual, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                                    srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && stats && gamma && beta && y, "groupnorm_apply: null argument");
+  SRGD_REQUIRE(B > 0 && Bx > 0 && Bx <= B && H > 0 && W > 0 && C > 0 && C % 64 == 0 && C <= 4096,
+               "groupnorm_apply: bad shape B=%d Bx=%d H=%d W=%d C=%d", B, Bx, H, W, C);
+  SRGD_REQUIRE(B <= 65535, "groupnorm_apply: B too large");
+  const int64_t total = (int64_t)H * W * (C / 8);
+  int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
+  if ((int64_t)gx * B > (int64_t)sm_count() * 16) gx = (sm_count() * 16 + B - 1) / B;
+  dim3 grid(gx, B);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
+  const bf16* xr = reinterpret_cast<const bf16*>(x);
+  const bf16* rr = reinterpret_cast<const bf16*>(residual);
+  bf16* yr = reinterpret_cast<bf16*>(y);
+  if (residual)
+    gn_apply_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride,
+                                                                  rr, yr, H * W, C);
+  else
+    gn_apply_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride,
+                                                                   rr, yr, H * W, C);
+  SRGD_LAUNCH_OK("gn_apply_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_pixel_inv_norm(const void* x, float* inv, int64_t M, int32_t C, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && inv && M > 0 && C >= 64 && C % 64 == 0, "pixel_inv_norm: bad arguments");
+  const bf16* xr = reinterpret_cast<const bf16*>(x);
+  if (C / 8 >= 32) {
+    const int grid = stream_grid((M + 7) / 8, 8);
+    pixel_inv_norm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+  } else if (C / 8 == 16) {
+    const int grid = stream_grid((M + 15) / 16, 8);
+    pixel_inv_norm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+  } else {
+    const int grid = stream_grid((M + 31) / 32, 8);
+    pixel_inv_norm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+  }
+  SRGD_LAUNCH_OK("pixel_inv_norm_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_rmsnorm_residual(const void* x, const float* g, const void* residual, void* y, int64_t M,
+                                     int32_t C, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && g && y && M > 0 && C >= 64 && C % 64 == 0 && C <= 1024, "rmsnorm_residual: bad arguments (C=%d)", C);
+  const bf16* xr = reinterpret_cast<const bf16*>(x);
+  const bf16* rr = reinterpret_cast<const bf16*>(residual);
+  bf16* yr = reinterpret_cast<bf16*>(y);
+  const float sc = sqrtf((float)C);
+  cudaStream_t st = as_stream(stream);
+#define SRGD_RMS(LP)                                                                                     \
+  do {                                                                                                   \
+    const int grid = stream_grid((M + (256 / LP) - 1) / (256 / LP), 8);                                  \
+    if (residual) rmsnorm_residual_kernel<LP, true><<<grid, 256, 0, st>>>(xr, g, rr, yr, M, C, sc);      \
+    else rmsnorm_residual_kernel<LP, false><<<grid, 256, 0, st>>>(xr, g, rr, yr, M, C, sc);              \
+  } while (0)
+  if (C / 8 >= 32) SRGD_RMS(32);
+  else if (C / 8 == 16) SRGD_RMS(16);
+  else SRGD_RMS(8);
+#undef SRGD_RMS
+  SRGD_LAUNCH_OK("rmsnorm_residual_kernel");
+  count_launch();
+  return SRGD_OK;
+}

@@ -1,0 +1,152 @@
+// Fused sampler-step kernels: CFG combine + x0 + clamp + posterior mean + noise add
+// (reference: model.py:3150/3154, 3160-3168, 3187-3188), q_sample (3434-3447), final clamp (3237).
+//
+// HBM-bound elementwise work on the fp32 NCHW sampler state.  Algorithmic bytes per element:
+// read x(4) + eps_cond(4) [+ eps_null(4)] [+ noise(4)], write img_next(4) [+ x_start(4)]
+// = 20 B (no CFG) / 24 B (CFG) with both optional outputs.
+// One float4 per thread per iteration, grid-stride, grid = multiple of the SM count.
+#include "common.cuh"
+
+namespace srgd {
+
+// One element of the update.  Written with explicit round-to-nearest intrinsics so that nvcc
+// does not contract a*b+c into FMA: the reference evaluates each torch op separately in fp32, and
+// the result here is bit-identical to that sequence.
+template <bool HAS_NULL, bool HAS_NOISE>
+__device__ __forceinline__ void step_elem(float x, float ec, float en, float z, const srgd_step_scalars& s,
+                                          float& out, float& x0) {
+  // eps = null + (cond - null) * s                          model.py:3150 / 3154
+  float eps = HAS_NULL ? __fadd_rn(en, __fmul_rn(__fsub_rn(ec, en), s.guidance_scale)) : ec;
+  // x_start = (x - sigma * eps) / alpha                     model.py:3160
+  float xs = __fdiv_rn(__fsub_rn(x, __fmul_rn(s.sigma, eps)), s.alpha);
+  float mean;
+  if (s.clip) {
+    xs = fminf(fmaxf(xs, -1.0f), 1.0f);                                       // model.py:3163
+    // alpha_next * (x * (1 - c) / alpha + c * x_start)     model.py:3164
+    float a = __fdiv_rn(__fmul_rn(x, __fsub_rn(1.0f, s.c)), s.alpha);
+    mean = __fmul_rn(s.alpha_next, __fadd_rn(a, __fmul_rn(s.c, xs)));
+  } else {
+    // alpha_next / alpha * (x - c * sigma * eps)            model.py:3166
+    mean = __fmul_rn(__fdiv_rn(s.alpha_next, s.alpha),
+                     __fsub_rn(x, __fmul_rn(__fmul_rn(s.c, s.sigma), eps)));
+  }
+  out = HAS_NOISE ? __fadd_rn(mean, __fmul_rn(s.noise_scale, z)) : mean;      // model.py:3188
+  x0 = xs;
+}
+
+template <bool HAS_NULL, bool HAS_NOISE, bool HAS_X0>
+__global__ void __launch_bounds__(256) sampler_step_kernel(
+    const float* __restrict__ x, const float* __restrict__ ec, const float* __restrict__ en,
+    const float* __restrict__ noise, float* img, float* __restrict__ x0out, int64_t n4, int64_t n,
+    srgd_step_scalars s) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 xv = ld_stream_f4(x + 4 * i);
+    float4 cv = ld_stream_f4(ec + 4 * i);
+    float4 nv = make_float4(0, 0, 0, 0), zv = make_float4(0, 0, 0, 0);
+    if (HAS_NULL) nv = ld_stream_f4(en + 4 * i);
+    if (HAS_NOISE) zv = ld_stream_f4(noise + 4 * i);
+    float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+    float na[4] = {nv.x, nv.y, nv.z, nv.w}, za[4] = {zv.x, zv.y, zv.z, zv.w};
+    float oa[4], sa[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) step_elem<HAS_NULL, HAS_NOISE>(xa[j], ca[j], na[j], za[j], s, oa[j], sa[j]);
+    st_stream_f4(img + 4 * i, make_float4(oa[0], oa[1], oa[2], oa[3]));
+    if (HAS_X0) st_stream_f4(x0out + 4 * i, make_float4(sa[0], sa[1], sa[2], sa[3]));
+  }
+  // scalar tail (n not a multiple of 4)
+  if (blockIdx.x == 0) {
+    for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+      float o, xs;
+      step_elem<HAS_NULL, HAS_NOISE>(x[i], ec[i], HAS_NULL ? en[i] : 0.f, HAS_NOISE ? noise[i] : 0.f, s, o, xs);
+      img[i] = o;
+      if (HAS_X0) x0out[i] = xs;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0,
+                                                       const float* __restrict__ noise, float* out,
+                                                       int64_t n, float alpha, float sigma) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = noise[i] * sigma;
+    if (x0) v = x0[i] * alpha + v;                                            // model.py:3442
+    out[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const float* img, float* out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = fminf(fmaxf(img[i], -1.0f), 1.0f);                              // model.py:3237
+    out[i] = (v + 1.0f) * 0.5f;                                               // model.py:44
+  }
+}
+
+static int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
+  int64_t want = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace srgd
+
+using namespace srgd;
+
+extern "C" int srgd_sampler_step(const float* x, const float* eps_cond, const float* eps_null,
+                                 const float* noise, float* img_next, float* x_start, int64_t n,
+                                 const srgd_step_scalars* s, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && eps_cond && img_next && s && n > 0, "srgd_sampler_step: null argument or n <= 0");
+  SRGD_REQUIRE(((uintptr_t)x | (uintptr_t)eps_cond | (uintptr_t)eps_null | (uintptr_t)noise |
+                (uintptr_t)img_next | (uintptr_t)x_start) % 16 == 0,
+               "srgd_sampler_step: pointers must be 16-byte aligned");
+  SRGD_REQUIRE(s->alpha > 0.f, "srgd_sampler_step: alpha must be > 0");
+  const int64_t n4 = n / 4;
+  const int grid = grid_for(n4, 256, 8);
+  cudaStream_t st = as_stream(stream);
+  const int key = (eps_null ? 4 : 0) | (noise ? 2 : 0) | (x_start ? 1 : 0);
+#define SRGD_CASE(K, A, B_, C)                                                                    \
+  case K:                                                                                         \
+    sampler_step_kernel<A, B_, C><<<grid, 256, 0, st>>>(x, eps_cond, eps_null, noise, img_next,   \
+                                                        x_start, n4, n, *s);                      \
+    break;
+  switch (key) {
+    SRGD_CASE(0, false, false, false)
+    SRGD_CASE(1, false, false, true)
+    SRGD_CASE(2, false, true, false)
+    SRGD_CASE(3, false, true, true)
+    SRGD_CASE(4, true, false, false)
+    SRGD_CASE(5, true, false, true)
+    SRGD_CASE(6, true, true, false)
+    SRGD_CASE(7, true, true, true)
+  }
+#undef SRGD_CASE
+  SRGD_LAUNCH_OK("sampler_step_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_q_sample(const float* x_start, const float* noise, float* out, int64_t n,
+                             float alpha, float sigma, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(noise && out && n > 0, "srgd_q_sample: null argument or n <= 0");
+  q_sample_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(x_start, noise, out, n, alpha, sigma);
+  SRGD_LAUNCH_OK("q_sample_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_finalize_image(const float* img, float* out, int64_t n, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(img && out && n > 0, "srgd_finalize_image: null argument or n <= 0");
+  finalize_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(img, out, n);
+  SRGD_LAUNCH_OK("finalize_kernel");
+  count_launch();
+  return SRGD_OK;
+}

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's `ConditionalSRUnet` (model.py:536-725).
+
+Same constructor keywords, attributes (`channels`, `self_condition`, `num_classes`,
+`random_or_learned_sinusoidal_cond`, `downsample_factor`), state-dict keys and
+`forward(x, time, class_label=None, x_self_cond=None) -> eps` contract.  The module owns fp32
+parameters only so that `load_state_dict(ckpt['ema_model'])`, `.to(device)` and `.eval()` behave
+like the reference's nn.Module; every FLOP of forward() runs in libsrgd_b200.so through
+`srgd_unet_forward` (tcgen05 implicit-GEMM convolutions, fused norm / attention kernels).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, weights
+from .arch import UnetSpec, unet_keys
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    node = root
+    for p in parts[:-1]:
+        if p not in node._modules:
+            node.add_module(p, _Node())
+        node = node._modules[p]
+    node.register_parameter(parts[-1], param)
+
+
+def _init_like_torch(name: str, shape: Tuple[int, ...], gen: torch.Generator) -> torch.Tensor:
+    """Random init in the spirit of torch's defaults (the reference relies on nn.Conv2d / nn.Linear
+    defaults); real use always loads a checkpoint over it."""
+    if name.endswith("time_mlp.0.weights") or name.endswith("class_mlp.0.weight"):
+        return torch.randn(shape, generator=gen)
+    if name.endswith(".g") or name.endswith("norm.weight"):
+        return torch.ones(shape)
+    if name.endswith("norm.bias"):
+        return torch.zeros(shape)
+    fan_in = 1
+    for s in (shape[1:] if len(shape) > 1 else shape):
+        fan_in *= s
+    if name.endswith(".bias"):
+        return torch.zeros(shape)
+    bound = (1.0 / fan_in) ** 0.5
+    return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+
+class ConditionalSRUnet(nn.Module):
+    def __init__(self, dim, init_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=3,
+                 self_condition=True, resnet_block_groups=8, learned_variance=False,
+                 learned_sinusoidal_cond=False, random_fourier_features=False, learned_sinusoidal_dim=16,
+                 attn_dim_head=32, attn_heads=4, full_attn=(False, False, False, True), flash_attn=False,
+                 pixel_shuffle_upsample=True, num_classes=None):
+        super().__init__()
+        unsupported = []
+        if init_dim not in (None, dim): unsupported.append("init_dim != dim")
+        if out_dim not in (None, channels): unsupported.append("out_dim")
+        if not self_condition: unsupported.append("self_condition=False")
+        if learned_variance: unsupported.append("learned_variance=True")
+        if not (learned_sinusoidal_cond or random_fourier_features):
+            unsupported.append("fixed sinusoidal time embedding")
+        if not pixel_shuffle_upsample: unsupported.append("pixel_shuffle_upsample=False")
+        if unsupported:
+            raise NotImplementedError("srgd_b200 builds the shipped conditional_continuous U-Net only; unsupported: "
+                                      + ", ".join(unsupported))
+        if isinstance(full_attn, bool):
+            full_attn = (full_attn,) * len(dim_mults)
+        assert len(full_attn) == len(dim_mults)
+        self.spec = UnetSpec(dim=dim, dim_mults=tuple(int(m) for m in dim_mults), channels=channels,
+                             groups=resnet_block_groups, learned_sinusoidal_dim=learned_sinusoidal_dim,
+                             heads=attn_heads, dim_head=attn_dim_head, full_attn=tuple(bool(f) for f in full_attn),
+                             num_classes=num_classes)
+        self.channels = channels
+        self.self_condition = self_condition
+        self.num_classes = num_classes
+        self.out_dim = channels
+        self.random_or_learned_sinusoidal_cond = True
+        self.downsample_factor = self.spec.downsample_factor
+        gen = torch.Generator().manual_seed(0)
+        for name, shape in unet_keys(self.spec).items():
+            p = nn.Parameter(_init_like_torch(name, shape, gen), requires_grad=False)
+            _attach(self, name, p)
+        self._handle = None
+        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._packed_key = None
+        self._workspaces: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self.conv_impl = 0          # debug knob: 1 = CUDA-core direct conv, 2 = stand-alone GN statistics
+        self.last_launches = 0
+
+    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspaces")
+
+    def __deepcopy__(self, memo):
+        # device handles / packed weights are per-instance runtime state: a copy re-packs lazily
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in self._RUNTIME_FIELDS else copy.deepcopy(v, memo)
+        new.__dict__["_workspaces"] = {}
+        return new
+
+    # -- parameter packing ---------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._drop_handle()
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        self._drop_handle()
+        return r
+
+    def _drop_handle(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().srgd_unet_destroy(self._handle)
+        self._handle = None
+        self._packed = None
+        self._workspaces = {}
+
+    def __del__(self):
+        try:
+            self._drop_handle()
+        except Exception:
+            pass
+
+    def _ensure_handle(self, device: torch.device):
+        if self._handle is not None and self._packed_key == device:
+            return
+        lib = _lib.load()
+        _lib.check(lib.srgd_device_check(device.index if device.index is not None else torch.cuda.current_device()),
+                   "srgd_device_check")
+        with torch.cuda.device(device):
+            sd = {k: v for k, v in self.state_dict().items()}
+            packed = weights.pack(self.spec, sd, device)
+            names = weights.param_names(self.spec)
+            missing = [n for n in names if n not in packed]
+            if missing:
+                raise _lib.SrgdError(f"weight packer did not produce {missing[:4]}...")
+            arr = (C.c_void_p * len(names))(*[packed[n].data_ptr() for n in names])
+            cfg = weights.make_config(self.spec)
+            handle = C.c_void_p()
+            _lib.check(lib.srgd_unet_create(C.byref(cfg), arr, len(names), C.byref(handle)), "srgd_unet_create")
+        self._handle, self._packed, self._packed_key = handle, packed, device
+        self._workspaces = {}
+
+    def _workspace(self, B: int, H: int, W: int, device) -> torch.Tensor:
+        key = (B, H, W)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = _lib.load().srgd_unet_workspace_bytes(self._handle, B, H, W)
+            if nbytes == 0:
+                raise _lib.SrgdError(f"unsupported U-Net input shape: {_lib.last_error()}")
+            # keep only the largest workspace alive; smaller shapes reuse it
+            big = max(self._workspaces.values(), key=lambda t: t.numel(), default=None)
+            if big is not None and big.numel() >= nbytes:
+                ws = big
+            else:
+                self._workspaces = {}
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspaces[key] = ws
+        return ws
+
+    # -- the hot call ----------------------------------------------------------------------------
+    def run(self, x: torch.Tensor, log_snr: torch.Tensor, labels_i32: Optional[torch.Tensor],
+            cond: Optional[torch.Tensor], rows: int, n_cond_rows: int, out: Optional[torch.Tensor] = None):
+        """eps[rows,3,H,W]; row b reads x[b % Bx] / cond[b % Bx] (cond only for b < n_cond_rows) with
+        label labels_i32[b] (<0 = null) and log_snr[b].  rows = Bx, or 2*Bx for the CFG pair."""
+        _lib.require_cuda(x, "ConditionalSRUnet")
+        Bx, _, H, W = x.shape
+        self._ensure_handle(x.device)
+        x = x.contiguous().float()
+        if cond is not None:
+            cond = cond.contiguous().float()
+        log_snr = log_snr.contiguous().float()
+        assert log_snr.numel() == rows and (labels_i32 is None or labels_i32.numel() == rows)
+        if out is None:
+            out = torch.empty(rows, self.channels, H, W, device=x.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            ws = self._workspace(rows, H, W, x.device)
+            rc = lib.srgd_unet_forward(self._handle, _lib.ptr(x), _lib.ptr(cond), _lib.ptr(log_snr),
+                                       _lib.ptr(labels_i32), n_cond_rows, Bx, _lib.ptr(out), rows, H, W,
+                                       _lib.ptr(ws), ws.numel(), int(self.conv_impl), _lib.current_stream())
+        _lib.check(rc, "srgd_unet_forward")
+        self.last_launches = lib.srgd_unet_last_launch_count(self._handle)
+        return out
+
+    def labels_for(self, class_label: Optional[torch.Tensor], rows: int, device) -> Optional[torch.Tensor]:
+        """int32 device labels for `rows` rows from the reference-style class_label ([B] or [1] int64)."""
+        if class_label is None or self.num_classes is None:
+            return None
+        lab = class_label.to(device=device).reshape(-1).to(torch.int32)
+        if lab.numel() == 1 and rows != 1:
+            lab = lab.expand(rows)
+        if lab.numel() != rows:
+            raise RuntimeError(f"class_label has {lab.numel()} entries for a batch of {rows}")
+        return lab.contiguous()
+
+    def forward(self, x, time, class_label=None, x_self_cond=None):
+        assert all(d % self.downsample_factor == 0 for d in x.shape[-2:]), \
+            f'your input dimensions {x.shape[-2:]} need to be divisible by {self.downsample_factor}, given the unet'
+        B = x.shape[0]
+        labels = self.labels_for(class_label, B, x.device)
+        return self.run(x, time.to(x.device).reshape(-1).expand(B) if time.numel() == 1 else time.to(x.device),
+                        labels, x_self_cond, B, B if x_self_cond is not None else 0)

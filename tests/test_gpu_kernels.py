@@ -1,0 +1,320 @@
+"""GPU parity tests of the individual CUDA kernels (C-ABI calls) against plain PyTorch fp32 math on
+the same bf16-rounded inputs (kernel-level) -- run with `pytest -m gpu` on a B200.
+
+Tolerances: kernels accumulate in fp32 and round the stored result to bf16 once, so the bound is
+bf16 rounding of the result (2^-8 relative) plus fp32 summation-order noise: 1e-2 * max|ref| abs.
+The sampler kernels are fp32 end to end and must match torch's op-by-op fp32 evaluation exactly.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from srgd_b200 import _lib  # noqa: E402
+import gpu_util as G  # noqa: E402
+from oracle import srgd_oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    l = _lib.load()
+    _lib.check(l.srgd_device_check(0), "device_check")
+    return l
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-6))
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("step,scale,has_noise", [(0, 1.0, True), (0, 3.0, True), (120, 3.0, True), (249, 3.0, False),
+                                                  (249, 1.0, False), (60, 1.0, True)])
+def test_sampler_step_exact(lib, step, scale, has_noise):
+    g = torch.Generator().manual_seed(step)
+    n = 3 * 64 * 64 * 2 + 3            # odd tail exercises the scalar path
+    x, ec, en, z = (torch.randn(n, generator=g) for _ in range(4))
+    steps = torch.linspace(1., 0., 251)
+    s = O.step_scalars(steps[step], steps[step + 1])
+    eps = en + (ec - en) * scale if scale != 1.0 else ec
+    mean, var, x0 = O.posterior_update(x, eps, s)
+    ref = mean + var.sqrt() * z if has_noise else mean
+    sc = _lib.StepScalars(float(s["alpha"]), float(s["sigma"]), float(s["alpha_next"]), float(s["c"]),
+                          float(s["var"].sqrt()) if has_noise else 0.0, scale, 1)
+    xd, ecd, end_, zd = (t.cuda() for t in (x, ec, en, z))
+    img, x0d = torch.empty_like(xd), torch.empty_like(xd)
+    _lib.check(lib.srgd_sampler_step(_lib.ptr(xd), _lib.ptr(ecd), _lib.ptr(end_) if scale != 1.0 else None,
+                                     _lib.ptr(zd) if has_noise else None, _lib.ptr(img), _lib.ptr(x0d), n,
+                                     C.byref(sc), G.stream()))
+    torch.cuda.synchronize()
+    # bit-exact against torch's separately rounded fp32 ops
+    assert torch.equal(x0d.cpu(), x0), float((x0d.cpu() - x0).abs().max())
+    assert torch.equal(img.cpu(), ref), float((img.cpu() - ref).abs().max())
+
+
+def test_q_sample_and_finalize(lib):
+    g = torch.Generator().manual_seed(3)
+    x0, z = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    out = torch.empty(1000, device="cuda")
+    _lib.check(lib.srgd_q_sample(_lib.ptr(x0.cuda()), _lib.ptr(z.cuda()), _lib.ptr(out), 1000, 0.6, 0.8, G.stream()))
+    torch.testing.assert_close(out.cpu(), x0 * 0.6 + z * 0.8, rtol=1e-6, atol=1e-6)
+    _lib.check(lib.srgd_q_sample(None, _lib.ptr(z.cuda()), _lib.ptr(out), 1000, 0.6, 0.8, G.stream()))
+    torch.testing.assert_close(out.cpu(), z * 0.8, rtol=0, atol=0)
+    img = (x0 * 2).cuda()
+    _lib.check(lib.srgd_finalize_image(_lib.ptr(img), _lib.ptr(out), 1000, G.stream()))
+    torch.testing.assert_close(out.cpu(), ((x0 * 2).clamp(-1, 1) + 1) * 0.5, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, H, W, [Cin...], Cout, ksize
+    (2, 32, 32, [128], 128, 3),
+    (1, 64, 64, [128], 128, 3),
+    (2, 16, 16, [256, 128], 256, 3),      # concat of two sources, BN=128/256
+    (2, 16, 16, [128], 384, 1),           # qkv-like 1x1
+    (3, 8, 8, [512], 1024, 3),            # tile spans 2 samples (TN=2), odd batch -> masked rows
+    (1, 40, 24, [128], 128, 3),           # partial tiles in x and y
+    (2, 32, 32, [64], 64, 3),             # BN=64 instance
+    (1, 32, 32, [1024, 512], 1024, 1),    # long-K 1x1 over a concat
+]
+
+
+@pytest.mark.parametrize("B,H,W,cins,Cout,ks", CONV_CASES)
+@pytest.mark.parametrize("direct", [False, True])
+def test_conv_matches_torch(lib, B, H, W, cins, Cout, ks, direct):
+    g = torch.Generator().manual_seed(B * 1000 + H + Cout)
+    xs = [G.bf16_round(torch.randn(B, c, H, W, generator=g)) for c in cins]
+    cin = sum(cins)
+    w = G.bf16_round(torch.randn(Cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks))
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(torch.cat(xs, 1), w, bias, padding=ks // 2)
+    out = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    d = G.plain_conv_desc([G.nhwc_bf16(x) for x in xs], G.pack_conv_weight(w), B, H, W, Cout, ks, out,
+                          bias=bias.cuda())
+    G.run_conv(d, direct)
+    got = G.to_nchw_f32(out)
+    assert rel_err(got, ref) < 1e-2, f"rel err {rel_err(got, ref)}"
+
+
+def test_conv_epilogue_variants(lib):
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cin, Cout = 2, 16, 16, 128, 512
+    x = G.bf16_round(torch.randn(B, Cin, H, W, generator=g))
+    w = G.bf16_round(torch.randn(Cout, Cin, 1, 1, generator=g) / math.sqrt(Cin))
+    bias = torch.randn(Cout, generator=g)
+    rs = torch.rand(B * H * W, generator=g) + 0.5
+    res = G.bf16_round(torch.randn(B, Cout, H, W, generator=g))
+    xd, wd = G.nhwc_bf16(x), G.pack_conv_weight(w)
+    # row scale + bias + residual
+    ref = F.conv2d(x, w) * rs.reshape(B, 1, H, W) + bias.reshape(1, -1, 1, 1) + res
+    for direct in (False, True):
+        out = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+        d = G.plain_conv_desc([xd], wd, B, H, W, Cout, 1, out, bias=bias.cuda(), row_scale=rs.cuda(),
+                              residual=G.nhwc_bf16(res))
+        G.run_conv(d, direct)
+        assert rel_err(G.to_nchw_f32(out), ref) < 1e-2, ("rowscale/residual", direct)
+    # SiLU + PixelShuffle(2): weights packed (i j c') as weights.py does
+    ref = F.pixel_shuffle(F.silu(F.conv2d(x, w, bias)), 2)
+    w_ps = w.reshape(Cout // 4, 4, Cin).permute(1, 0, 2).reshape(Cout, Cin, 1, 1)
+    b_ps = bias.reshape(Cout // 4, 4).permute(1, 0).reshape(Cout)
+    for direct in (False, True):
+        out = torch.zeros(B, 2 * H, 2 * W, Cout // 4, device="cuda", dtype=torch.bfloat16)
+        d = G.plain_conv_desc([xd], G.pack_conv_weight(w_ps), B, H, W, Cout, 1, out, bias=b_ps.cuda(), act=1,
+                              out_mode=_lib.OUT_PIXEL_SHUFFLE)
+        G.run_conv(d, direct)
+        assert rel_err(G.to_nchw_f32(out), ref) < 1e-2, ("pixelshuffle", direct)
+
+
+def test_conv_downsample_as_strided_sources(lib):
+    g = torch.Generator().manual_seed(6)
+    B, H, W, Cin, Cout = 2, 32, 32, 128, 256
+    x = G.bf16_round(torch.randn(B, Cin, H, W, generator=g))
+    w = G.bf16_round(torch.randn(Cout, 4 * Cin, 1, 1, generator=g) / math.sqrt(4 * Cin))
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(F.pixel_unshuffle(x, 2), w, bias)            # 'b c (h p1) (w p2) -> b (c p1 p2) h w'
+    wp = w.reshape(Cout, Cin, 2, 2).permute(0, 2, 3, 1).reshape(Cout, 4 * Cin).contiguous().cuda().bfloat16()
+    xd = G.nhwc_bf16(x)
+    Ho, Wo = H // 2, W // 2
+    srcs, phases = [], []
+    for i in range(4):
+        p1, p2 = i >> 1, i & 1
+        srcs.append((xd.data_ptr() + (p1 * W + p2) * Cin * 2, H * W * Cin, 2 * W * Cin, 2 * Cin, Ho, Wo, Cin))
+        phases.append((i, 0, 0, i * Cin))
+    for direct in (False, True):
+        out = torch.zeros(B, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+        d = G.conv_desc(srcs, phases, wp, 4 * Cin, B, Ho, Wo, Cout, out, bias=bias.cuda())
+        G.run_conv(d, direct)
+        assert rel_err(G.to_nchw_f32(out), ref) < 1e-2, direct
+
+
+def test_init_conv_pack_and_7tap(lib):
+    g = torch.Generator().manual_seed(7)
+    B, H, W, Cout = 2, 32, 48, 128
+    x, cond = torch.randn(B, 3, H, W, generator=g), torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    w = torch.randn(Cout, 6, 7, 7, generator=g) / math.sqrt(6 * 49)
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(G.bf16_round(torch.cat((x, cond), 1)), G.bf16_round(w), bias, padding=3)
+    pk = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.srgd_pack_input(_lib.ptr(x.cuda()), _lib.ptr(cond.cuda()), B, B, _lib.ptr(pk), B, H, W, G.stream()))
+    wi = torch.zeros(Cout, 7, 64)
+    wi[:, :, :42] = w.permute(0, 2, 3, 1).reshape(Cout, 7, 42)
+    wp = wi.reshape(Cout, 7 * 64).cuda().bfloat16().contiguous()
+    out = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    d = G.conv_desc([(pk, H * W * 64, W * 64, 64, H, W, 64)], [(0, i - 3, 0, i * 64) for i in range(7)], wp, 7 * 64,
+                    B, H, W, Cout, out, bias=bias.cuda())
+    G.run_conv(d)
+    assert rel_err(G.to_nchw_f32(out), ref) < 1e-2
+    # null condition rows (x_self_cond=None -> zeros) and the CFG row mapping b % Bx
+    pk2 = torch.empty(2 * B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.srgd_pack_input(_lib.ptr(x.cuda()), _lib.ptr(cond.cuda()), B, B, _lib.ptr(pk2), 2 * B, H, W,
+                                   G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(pk2[:B], pk)
+    ch = torch.arange(64, device="cuda")
+    is_cond = ((ch % 6) >= 3) & (ch < 42)
+    assert float(pk2[B:][..., is_cond].float().abs().max()) == 0.0
+    assert torch.equal(pk2[B:][..., ~is_cond], pk[..., ~is_cond])
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm / RMSNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64)])
+def test_groupnorm_fused_stats_and_apply(lib, B, H, W, C):
+    g = torch.Generator().manual_seed(C + H)
+    Cin = 128
+    x = G.bf16_round(torch.randn(B, Cin, H, W, generator=g))
+    w = G.bf16_round(torch.randn(C, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    bias = torch.randn(C, generator=g) * 0.5
+    conv = F.conv2d(x, w, bias, padding=1)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ss = torch.randn(B, 2 * C + 7, generator=g) * 0.3             # row stride != 2C on purpose
+    resid = G.bf16_round(torch.randn(B, C, H, W, generator=g))
+    mt = lib.srgd_conv_m_tiles(B, H, W)
+    part = torch.full((mt * 4 * 8 * 2,), float("nan"), device="cuda")
+    out = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
+    d = G.plain_conv_desc([G.nhwc_bf16(x)], G.pack_conv_weight(w), B, H, W, C, 3, out, bias=bias.cuda(),
+                          gn_partials=part)
+    G.run_conv(d)
+    stats = torch.empty(B * 8 * 2, device="cuda")
+    _lib.check(lib.srgd_groupnorm_finalize(_lib.ptr(part), _lib.ptr(stats), B, H, W, C, G.stream()))
+    grp = conv.reshape(B, 8, -1)
+    ref_mean, ref_rstd = grp.mean(-1), (grp.var(-1, unbiased=False) + 1e-5).rsqrt()
+    st = stats.cpu().reshape(B, 8, 2)
+    torch.testing.assert_close(st[..., 0], ref_mean, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(st[..., 1], ref_rstd, rtol=1e-3, atol=1e-4)
+    # stand-alone statistics kernel agrees (computed from the bf16-rounded conv output)
+    stats2 = torch.empty_like(stats)
+    _lib.check(lib.srgd_groupnorm_stats(_lib.ptr(out), _lib.ptr(stats2), B, H, W, C, G.stream()))
+    torch.testing.assert_close(stats2.cpu().reshape(B, 8, 2)[..., 0], ref_mean, rtol=1e-2, atol=2e-3)
+    # apply: GN affine, (scale+1, shift), SiLU, + residual -- reference evaluated on the bf16 conv output
+    conv_b = G.to_nchw_f32(out)
+    scale, shift = ss[:, :C], ss[:, C:2 * C]
+    y = F.group_norm(conv_b, 8, gamma, beta, eps=1e-5)
+    y = F.silu(y * (scale[:, :, None, None] + 1) + shift[:, :, None, None]) + resid
+    yd = torch.empty_like(out)
+    _lib.check(lib.srgd_groupnorm_apply(_lib.ptr(out), B, _lib.ptr(stats), _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()),
+                                        _lib.ptr(ss.cuda()), 2 * C + 7, _lib.ptr(G.nhwc_bf16(resid)), _lib.ptr(yd),
+                                        B, H, W, C, G.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(G.to_nchw_f32(yd), y) < 1.5e-2
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512, 1024])
+def test_rmsnorm_kernels(lib, C):
+    g = torch.Generator().manual_seed(C)
+    M = 777
+    x = G.bf16_round(torch.randn(M, C, generator=g) * 2)
+    gain = 1 + 0.1 * torch.randn(C, generator=g)
+    res = G.bf16_round(torch.randn(M, C, generator=g))
+    inv = torch.empty(M, device="cuda")
+    xd = x.cuda().bfloat16()
+    _lib.check(lib.srgd_pixel_inv_norm(_lib.ptr(xd), _lib.ptr(inv), M, C, G.stream()))
+    torch.testing.assert_close(inv.cpu(), 1.0 / x.norm(dim=1).clamp(min=1e-12), rtol=1e-5, atol=1e-7)
+    ref = F.normalize(x, dim=1) * gain * math.sqrt(C) + res
+    y = torch.empty_like(xd)
+    _lib.check(lib.srgd_rmsnorm_residual(_lib.ptr(xd), _lib.ptr(gain.cuda()), _lib.ptr(res.cuda().bfloat16()),
+                                         _lib.ptr(y), M, C, G.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(y.float().cpu(), ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# attention cores
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(2, 1024), (1, 4096), (3, 200)])
+def test_linear_attention_core(lib, B, N):
+    g = torch.Generator().manual_seed(N)
+    qkv = G.bf16_round(torch.randn(B, N, 384, generator=g) * 1.5)
+    q, k, v = (t.reshape(B, N, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=-1))   # b h d n
+    qs, ks = q.softmax(dim=-2) * 32 ** -0.5, k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", ks, v)
+    ref = torch.einsum("bhde,bhdn->bhen", ctx, qs).permute(0, 3, 1, 2).reshape(B, N, 128)
+    out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
+    wsb = lib.srgd_linear_attention_workspace(B, N, 4)
+    ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.srgd_linear_attention(_lib.ptr(qkv.cuda().bfloat16()), _lib.ptr(out), B, N, 4, _lib.ptr(ws), wsb,
+                                         G.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,N", [(2, 1024), (1, 64), (2, 100)])
+def test_full_attention_core(lib, B, N):
+    g = torch.Generator().manual_seed(N + 1)
+    qkv = G.bf16_round(torch.randn(B, N, 384, generator=g) * 1.5)
+    q, k, v = (t.reshape(B, N, 4, 32).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))   # b h n d
+    ref = O._attend(q, k, v).permute(0, 2, 1, 3).reshape(B, N, 128)
+    out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.srgd_attention(_lib.ptr(qkv.cuda().bfloat16()), _lib.ptr(out), B, N, 4, G.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# small dense layers / embeddings / final conv
+# ------------------------------------------------------------------------------------------------
+def test_embedding_kernels(lib):
+    g = torch.Generator().manual_seed(11)
+    B = 5
+    lsnr = torch.tensor([-10.0, -3.3, 0.1, 4.4, 9.2])
+    wts = torch.randn(16, generator=g)
+    feats = torch.empty(B, 33, device="cuda")
+    _lib.check(lib.srgd_fourier_features(_lib.ptr(lsnr.cuda()), _lib.ptr(wts.cuda()), _lib.ptr(feats), B, 16, G.stream()))
+    fr = lsnr[:, None] * wts[None, :] * 2 * math.pi
+    ref = torch.cat((lsnr[:, None], fr.sin(), fr.cos()), -1)
+    torch.testing.assert_close(feats.cpu(), ref, rtol=0, atol=2e-5)
+    for act, fn in ((0, lambda t: t), (1, F.silu), (2, F.gelu)):
+        x, w, b = torch.randn(B, 512, generator=g), torch.randn(300, 512, generator=g) / 22, torch.randn(300, generator=g)
+        y = torch.empty(B, 300, device="cuda")
+        _lib.check(lib.srgd_dense_rows(_lib.ptr(x.cuda()), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), _lib.ptr(y), B, 300,
+                                       512, act, 0, G.stream()))
+        torch.testing.assert_close(y.cpu(), F.linear(fn(x), w, b), rtol=1e-4, atol=1e-4)
+    t = torch.randn(B, 512, generator=g)
+    table = torch.randn(3, 512, generator=g)
+    labels = torch.tensor([0, -1, 2, 1, -1], dtype=torch.int32)
+    td = t.cuda()
+    _lib.check(lib.srgd_add_class_rows(_lib.ptr(td), _lib.ptr(table.cuda()), _lib.ptr(labels.cuda()), B, 512, 3, G.stream()))
+    ref = t.clone()
+    for i, l in enumerate(labels.tolist()):
+        if l >= 0:
+            ref[i] += table[l]
+    torch.testing.assert_close(td.cpu(), ref, rtol=0, atol=0)
+
+
+def test_final_conv(lib):
+    g = torch.Generator().manual_seed(12)
+    B, H, W, Cc = 2, 16, 24, 128
+    h = G.bf16_round(torch.randn(B, Cc, H, W, generator=g))
+    w, b = torch.randn(3, Cc, generator=g) / 11, torch.randn(3, generator=g)
+    eps = torch.empty(B, 3, H, W, device="cuda")
+    _lib.check(lib.srgd_final_conv(_lib.ptr(G.nhwc_bf16(h)), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), _lib.ptr(eps), B, H,
+                                   W, Cc, 3, G.stream()))
+    torch.testing.assert_close(eps.cpu(), F.conv2d(h, w.reshape(3, Cc, 1, 1), b), rtol=1e-4, atol=1e-4)

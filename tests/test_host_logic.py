@@ -1,0 +1,171 @@
+"""CPU-only tests: host logic, the C-ABI surface, the drop-in module names.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from srgd_b200 import _lib, arch, tiling
+from oracle import srgd_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "srgd_b200.h")).read()
+    declared = set(re.findall(r"\b(srgd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"srgd_b200"}
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/srgd_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().srgd_version() == 100
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs the real header: sizeof/offsetof printed by a gcc-compiled probe."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    probe = tmp_path / "probe.c"
+    probe.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "srgd_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu ", sizeof(srgd_step_scalars), sizeof(srgd_conv_src), sizeof(srgd_conv_phase),
+         sizeof(srgd_conv_desc), sizeof(srgd_unet_config));
+  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(srgd_conv_desc, srcs), offsetof(srgd_conv_desc, phases),
+         offsetof(srgd_conv_desc, weight), offsetof(srgd_conv_desc, act), offsetof(srgd_conv_desc, gn_partials),
+         offsetof(srgd_unet_config, heads));
+  return 0;
+}''')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    D, U = _lib.ConvDesc, _lib.UnetConfig
+    want = [C.sizeof(_lib.StepScalars), C.sizeof(_lib.ConvSrc), C.sizeof(_lib.ConvPhase), C.sizeof(D), C.sizeof(U),
+            D.srcs.offset, D.phases.offset, D.weight.offset, D.act.offset, D.gn_partials.offset, U.heads.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point fails loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    s = _lib.StepScalars(1, 1, 1, 0.5, 0, 1, 1)
+    buf = (C.c_float * 8)()
+    rc = lib.srgd_sampler_step(buf, buf, None, None, buf, None, 8, C.byref(s), None)
+    assert rc == -2 and "no CPU fallback" in _lib.last_error()
+    import model as M
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unet(torch.zeros(1, 3, 64, 64), torch.zeros(1))
+
+
+def test_product_package_never_imports_oracle():
+    for base in ("srgd_b200", "."):
+        d = os.path.join(ROOT, base)
+        for f in os.listdir(d):
+            if f.endswith(".py") and f not in ("bench.py", "__graft_entry__.py"):
+                src = open(os.path.join(d, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{base}/{f} mentions the oracle"
+
+
+def test_state_dict_layout_matches_reference_checkpoint():
+    import model as M
+    spec = O.UnetSpec()
+    unet = M.ConditionalSRUnet(dim=128, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=256)
+    want = O.param_shapes(spec)                       # pinned to the reference by make_golden.py
+    got = diff.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    assert all(tuple(got[k].shape) == v for k, v in want.items())
+    sd = O.make_state_dict(O.UnetSpec(dim=64), 3)
+    small = M.ConditionalContinuousTimeGaussianDiffusionSR(
+        model=M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3),
+        image_size=64)
+    small.load_state_dict(sd, strict=True)
+    bad = dict(sd)
+    bad.pop("model.final_conv.bias")
+    with pytest.raises(RuntimeError):
+        small.load_state_dict(bad, strict=True)
+
+
+def test_packing_contract_names():
+    from srgd_b200 import weights
+    names = weights.param_names(arch.UnetSpec())
+    assert names[0] == "init.w" and names[-1] == "final.b" and "class.table" in names
+    assert len(names) == len(set(names))
+    assert "ups.0.0.res.w" in names and "downs.0.0.res.w" not in names
+
+
+def test_get_model_and_checkpoint_roundtrip(tmp_path):
+    import config
+    import logging
+    import model as M
+    yaml_path = tmp_path / "c.yaml"
+    yaml_path.write_text("model: conditional_continuous\nunet_dim: 64\nimage_size: 64\nnum_sample_steps: 250\n"
+                         "learned_sinusoidal_cond: true\nlearned_sinusoidal_dim: 32\nlr: 1e-4\n")
+    conf = config.load_config(str(yaml_path))
+    assert conf.lr == "1e-4" and conf.num_classes == 3        # PyYAML 1.1 float quirk kept
+    sd = O.make_state_dict(O.UnetSpec(dim=64), 5)
+    ck = tmp_path / "w.pth"
+    torch.save({"ema_model": sd}, ck)
+    conf.ckpt_path = str(ck)
+    ema = M.get_model(conf, logging.getLogger("t"))
+    got = ema.module.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in sd.items())
+    assert ema.module.model.downsample_factor == 8 and ema.module.image_size == 64
+    with pytest.raises(TypeError):
+        config.Config(not_a_field=1)
+    conf.model = "elucidated"
+    with pytest.raises(NotImplementedError):
+        M.get_model(conf, logging.getLogger("t"))
+    with pytest.raises(ValueError):
+        M.ConditionalContinuousTimeGaussianDiffusionSR(model=ema.module.model, image_size=64, noise_schedule="nope")
+
+
+def test_shipped_yaml_loads():
+    ref_yaml = "/root/reference/conf/conditional_continuous_linear_df8kost_dim128.yaml"
+    if not os.path.exists(ref_yaml):
+        pytest.skip("reference checkout not present on this box")
+    import config
+    conf = config.load_config(ref_yaml)
+    assert (conf.model, conf.unet_dim, conf.image_size, conf.num_sample_steps) == ("conditional_continuous", 128, 256, 250)
+
+
+def test_step_scalars_match_oracle():
+    import model as M
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=64)
+    steps = torch.linspace(1., 0., 251)
+    for i in (0, 1, 77, 248, 249):
+        s = diff.step_scalars(steps[i], steps[i + 1])
+        o = O.step_scalars(steps[i], steps[i + 1])
+        assert s.alpha == float(o["alpha"]) and s.sigma == float(o["sigma"]) and s.c == float(o["c"])
+        assert s.alpha_next == float(o["alpha_next"])
+        assert s.noise_scale == (float(o["var"].sqrt()) if i < 249 else 0.0)
+
+
+def test_tile_plan_counts():
+    p = tiling.TilePlan(2048, 2048)
+    assert (p.canvas_h, p.canvas_w, len(p.grids[0]), len(p.grids[1])) == (2304, 2304, 81, 64)
+    assert p.tiles_per_image(250) == 18125                     # BASELINE.md work table
+    assert tiling.TilePlan(512, 512).tiles_per_image(250) == 1625
+    assert tiling.TilePlan(256, 256).tiles_per_image(250) == 250
+
+
+def test_inference_cli_flags():
+    import inference
+    a = inference.parse_args(["-c", "x.yaml", "-m", "w.pth", "--input_dir", "i", "--output_dir", "o"])
+    assert (a.batch_size, a.num_sample_steps, a.interpolation, a.cond_scale, a.class_cond_scale) == (8, 250, "bicubic", 1.0, 1.0)
+    assert (a.guidance_start_steps, a.class_guidance_start_steps, a.generation_start_steps) == (0, 0, 0)
+    assert (a.start_index, a.end_index, a.test_label, a.seed, a.backend, a.amp, a.use_dpmpp_solver) == \
+        (0, None, None, 71, "ddp", True, True)
+    a = inference.parse_args(["-c", "x", "-m", "w", "--input_dir", "i", "--output_dir", "o", "--class_cond_scale", "3.0",
+                              "--test_label", "2", "--seed", "5", "--no_amp"])
+    assert a.class_cond_scale == 3.0 and a.test_label == 2 and a.seed == 5 and a.amp is False
