@@ -6,6 +6,22 @@ import torch
 from srgd_b200 import _lib
 
 
+_alive = []
+
+
+def P(t):
+    """Device pointer of `t`, keeping `t` alive until release() (ctypes pointers do not own storage)."""
+    if t is None:
+        return None
+    _alive.append(t)
+    return _lib.ptr(t)
+
+
+def release():
+    torch.cuda.synchronize()
+    _alive.clear()
+
+
 def stream():
     return _lib.current_stream()
 
@@ -42,6 +58,7 @@ def conv_desc(srcs, phases, weight, Ktot, B, Ho, Wo, Cout, out, bias=None, row_s
     d.act, d.out_mode = act, out_mode
     d.out = out.data_ptr()
     d.gn_partials = gn_partials.data_ptr() if gn_partials is not None else None
+    d._keep = [srcs, weight, out, bias, row_scale, residual, gn_partials]     # keep the storages alive
     return d
 
 

@@ -26,6 +26,12 @@ def lib():
     return l
 
 
+@pytest.fixture(autouse=True)
+def _release_kept_tensors():
+    yield
+    G.release()
+
+
 def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-6))
 
@@ -48,8 +54,8 @@ def test_sampler_step_exact(lib, step, scale, has_noise):
                           float(s["var"].sqrt()) if has_noise else 0.0, scale, 1)
     xd, ecd, end_, zd = (t.cuda() for t in (x, ec, en, z))
     img, x0d = torch.empty_like(xd), torch.empty_like(xd)
-    _lib.check(lib.srgd_sampler_step(_lib.ptr(xd), _lib.ptr(ecd), _lib.ptr(end_) if scale != 1.0 else None,
-                                     _lib.ptr(zd) if has_noise else None, _lib.ptr(img), _lib.ptr(x0d), n,
+    _lib.check(lib.srgd_sampler_step(G.P(xd), G.P(ecd), G.P(end_) if scale != 1.0 else None,
+                                     G.P(zd) if has_noise else None, G.P(img), G.P(x0d), n,
                                      C.byref(sc), G.stream()))
     torch.cuda.synchronize()
     # bit-exact against torch's separately rounded fp32 ops
@@ -61,12 +67,13 @@ def test_q_sample_and_finalize(lib):
     g = torch.Generator().manual_seed(3)
     x0, z = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
     out = torch.empty(1000, device="cuda")
-    _lib.check(lib.srgd_q_sample(_lib.ptr(x0.cuda()), _lib.ptr(z.cuda()), _lib.ptr(out), 1000, 0.6, 0.8, G.stream()))
+    x0d, zd = x0.cuda(), z.cuda()          # keep references: ctypes pointers do not own the storage
+    _lib.check(lib.srgd_q_sample(G.P(x0d), G.P(zd), G.P(out), 1000, 0.6, 0.8, G.stream()))
     torch.testing.assert_close(out.cpu(), x0 * 0.6 + z * 0.8, rtol=1e-6, atol=1e-6)
-    _lib.check(lib.srgd_q_sample(None, _lib.ptr(z.cuda()), _lib.ptr(out), 1000, 0.6, 0.8, G.stream()))
+    _lib.check(lib.srgd_q_sample(None, G.P(zd), G.P(out), 1000, 0.6, 0.8, G.stream()))
     torch.testing.assert_close(out.cpu(), z * 0.8, rtol=0, atol=0)
     img = (x0 * 2).cuda()
-    _lib.check(lib.srgd_finalize_image(_lib.ptr(img), _lib.ptr(out), 1000, G.stream()))
+    _lib.check(lib.srgd_finalize_image(G.P(img), G.P(out), 1000, G.stream()))
     torch.testing.assert_close(out.cpu(), ((x0 * 2).clamp(-1, 1) + 1) * 0.5, rtol=0, atol=0)
 
 
@@ -162,7 +169,7 @@ def test_init_conv_pack_and_7tap(lib):
     bias = torch.randn(Cout, generator=g)
     ref = F.conv2d(G.bf16_round(torch.cat((x, cond), 1)), G.bf16_round(w), bias, padding=3)
     pk = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.srgd_pack_input(_lib.ptr(x.cuda()), _lib.ptr(cond.cuda()), B, B, _lib.ptr(pk), B, H, W, G.stream()))
+    _lib.check(lib.srgd_pack_input(G.P(x.cuda()), G.P(cond.cuda()), B, B, G.P(pk), B, H, W, G.stream()))
     wi = torch.zeros(Cout, 7, 64)
     wi[:, :, :42] = w.permute(0, 2, 3, 1).reshape(Cout, 7, 42)
     wp = wi.reshape(Cout, 7 * 64).cuda().bfloat16().contiguous()
@@ -173,7 +180,7 @@ def test_init_conv_pack_and_7tap(lib):
     assert rel_err(G.to_nchw_f32(out), ref) < 1e-2
     # null condition rows (x_self_cond=None -> zeros) and the CFG row mapping b % Bx
     pk2 = torch.empty(2 * B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.srgd_pack_input(_lib.ptr(x.cuda()), _lib.ptr(cond.cuda()), B, B, _lib.ptr(pk2), 2 * B, H, W,
+    _lib.check(lib.srgd_pack_input(G.P(x.cuda()), G.P(cond.cuda()), B, B, G.P(pk2), 2 * B, H, W,
                                    G.stream()))
     torch.cuda.synchronize()
     assert torch.equal(pk2[:B], pk)
@@ -204,7 +211,7 @@ def test_groupnorm_fused_stats_and_apply(lib, B, H, W, C):
                           gn_partials=part)
     G.run_conv(d)
     stats = torch.empty(B * 8 * 2, device="cuda")
-    _lib.check(lib.srgd_groupnorm_finalize(_lib.ptr(part), _lib.ptr(stats), B, H, W, C, G.stream()))
+    _lib.check(lib.srgd_groupnorm_finalize(G.P(part), G.P(stats), B, H, W, C, G.stream()))
     grp = conv.reshape(B, 8, -1)
     ref_mean, ref_rstd = grp.mean(-1), (grp.var(-1, unbiased=False) + 1e-5).rsqrt()
     st = stats.cpu().reshape(B, 8, 2)
@@ -212,7 +219,7 @@ def test_groupnorm_fused_stats_and_apply(lib, B, H, W, C):
     torch.testing.assert_close(st[..., 1], ref_rstd, rtol=1e-3, atol=1e-4)
     # stand-alone statistics kernel agrees (computed from the bf16-rounded conv output)
     stats2 = torch.empty_like(stats)
-    _lib.check(lib.srgd_groupnorm_stats(_lib.ptr(out), _lib.ptr(stats2), B, H, W, C, G.stream()))
+    _lib.check(lib.srgd_groupnorm_stats(G.P(out), G.P(stats2), B, H, W, C, G.stream()))
     torch.testing.assert_close(stats2.cpu().reshape(B, 8, 2)[..., 0], ref_mean, rtol=1e-2, atol=2e-3)
     # apply: GN affine, (scale+1, shift), SiLU, + residual -- reference evaluated on the bf16 conv output
     conv_b = G.to_nchw_f32(out)
@@ -220,8 +227,8 @@ def test_groupnorm_fused_stats_and_apply(lib, B, H, W, C):
     y = F.group_norm(conv_b, 8, gamma, beta, eps=1e-5)
     y = F.silu(y * (scale[:, :, None, None] + 1) + shift[:, :, None, None]) + resid
     yd = torch.empty_like(out)
-    _lib.check(lib.srgd_groupnorm_apply(_lib.ptr(out), B, _lib.ptr(stats), _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()),
-                                        _lib.ptr(ss.cuda()), 2 * C + 7, _lib.ptr(G.nhwc_bf16(resid)), _lib.ptr(yd),
+    _lib.check(lib.srgd_groupnorm_apply(G.P(out), B, G.P(stats), G.P(gamma.cuda()), G.P(beta.cuda()),
+                                        G.P(ss.cuda()), 2 * C + 7, G.P(G.nhwc_bf16(resid)), G.P(yd),
                                         B, H, W, C, G.stream()))
     torch.cuda.synchronize()
     assert rel_err(G.to_nchw_f32(yd), y) < 1.5e-2
@@ -236,12 +243,12 @@ def test_rmsnorm_kernels(lib, C):
     res = G.bf16_round(torch.randn(M, C, generator=g))
     inv = torch.empty(M, device="cuda")
     xd = x.cuda().bfloat16()
-    _lib.check(lib.srgd_pixel_inv_norm(_lib.ptr(xd), _lib.ptr(inv), M, C, G.stream()))
+    _lib.check(lib.srgd_pixel_inv_norm(G.P(xd), G.P(inv), M, C, G.stream()))
     torch.testing.assert_close(inv.cpu(), 1.0 / x.norm(dim=1).clamp(min=1e-12), rtol=1e-5, atol=1e-7)
     ref = F.normalize(x, dim=1) * gain * math.sqrt(C) + res
     y = torch.empty_like(xd)
-    _lib.check(lib.srgd_rmsnorm_residual(_lib.ptr(xd), _lib.ptr(gain.cuda()), _lib.ptr(res.cuda().bfloat16()),
-                                         _lib.ptr(y), M, C, G.stream()))
+    _lib.check(lib.srgd_rmsnorm_residual(G.P(xd), G.P(gain.cuda()), G.P(res.cuda().bfloat16()),
+                                         G.P(y), M, C, G.stream()))
     torch.cuda.synchronize()
     assert rel_err(y.float().cpu(), ref) < 1e-2
 
@@ -260,7 +267,7 @@ def test_linear_attention_core(lib, B, N):
     out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
     wsb = lib.srgd_linear_attention_workspace(B, N, 4)
     ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
-    _lib.check(lib.srgd_linear_attention(_lib.ptr(qkv.cuda().bfloat16()), _lib.ptr(out), B, N, 4, _lib.ptr(ws), wsb,
+    _lib.check(lib.srgd_linear_attention(G.P(qkv.cuda().bfloat16()), G.P(out), B, N, 4, G.P(ws), wsb,
                                          G.stream()))
     torch.cuda.synchronize()
     assert rel_err(out.float().cpu(), ref) < 1e-2
@@ -273,7 +280,7 @@ def test_full_attention_core(lib, B, N):
     q, k, v = (t.reshape(B, N, 4, 32).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))   # b h n d
     ref = O._attend(q, k, v).permute(0, 2, 1, 3).reshape(B, N, 128)
     out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.srgd_attention(_lib.ptr(qkv.cuda().bfloat16()), _lib.ptr(out), B, N, 4, G.stream()))
+    _lib.check(lib.srgd_attention(G.P(qkv.cuda().bfloat16()), G.P(out), B, N, 4, G.stream()))
     torch.cuda.synchronize()
     assert rel_err(out.float().cpu(), ref) < 1e-2
 
@@ -287,21 +294,21 @@ def test_embedding_kernels(lib):
     lsnr = torch.tensor([-10.0, -3.3, 0.1, 4.4, 9.2])
     wts = torch.randn(16, generator=g)
     feats = torch.empty(B, 33, device="cuda")
-    _lib.check(lib.srgd_fourier_features(_lib.ptr(lsnr.cuda()), _lib.ptr(wts.cuda()), _lib.ptr(feats), B, 16, G.stream()))
+    _lib.check(lib.srgd_fourier_features(G.P(lsnr.cuda()), G.P(wts.cuda()), G.P(feats), B, 16, G.stream()))
     fr = lsnr[:, None] * wts[None, :] * 2 * math.pi
     ref = torch.cat((lsnr[:, None], fr.sin(), fr.cos()), -1)
     torch.testing.assert_close(feats.cpu(), ref, rtol=0, atol=2e-5)
     for act, fn in ((0, lambda t: t), (1, F.silu), (2, F.gelu)):
         x, w, b = torch.randn(B, 512, generator=g), torch.randn(300, 512, generator=g) / 22, torch.randn(300, generator=g)
         y = torch.empty(B, 300, device="cuda")
-        _lib.check(lib.srgd_dense_rows(_lib.ptr(x.cuda()), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), _lib.ptr(y), B, 300,
+        _lib.check(lib.srgd_dense_rows(G.P(x.cuda()), G.P(w.cuda()), G.P(b.cuda()), G.P(y), B, 300,
                                        512, act, 0, G.stream()))
         torch.testing.assert_close(y.cpu(), F.linear(fn(x), w, b), rtol=1e-4, atol=1e-4)
     t = torch.randn(B, 512, generator=g)
     table = torch.randn(3, 512, generator=g)
     labels = torch.tensor([0, -1, 2, 1, -1], dtype=torch.int32)
     td = t.cuda()
-    _lib.check(lib.srgd_add_class_rows(_lib.ptr(td), _lib.ptr(table.cuda()), _lib.ptr(labels.cuda()), B, 512, 3, G.stream()))
+    _lib.check(lib.srgd_add_class_rows(G.P(td), G.P(table.cuda()), G.P(labels.cuda()), B, 512, 3, G.stream()))
     ref = t.clone()
     for i, l in enumerate(labels.tolist()):
         if l >= 0:
@@ -315,6 +322,6 @@ def test_final_conv(lib):
     h = G.bf16_round(torch.randn(B, Cc, H, W, generator=g))
     w, b = torch.randn(3, Cc, generator=g) / 11, torch.randn(3, generator=g)
     eps = torch.empty(B, 3, H, W, device="cuda")
-    _lib.check(lib.srgd_final_conv(_lib.ptr(G.nhwc_bf16(h)), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), _lib.ptr(eps), B, H,
+    _lib.check(lib.srgd_final_conv(G.P(G.nhwc_bf16(h)), G.P(w.cuda()), G.P(b.cuda()), G.P(eps), B, H,
                                    W, Cc, 3, G.stream()))
     torch.testing.assert_close(eps.cpu(), F.conv2d(h, w.reshape(3, Cc, 1, 1), b), rtol=1e-4, atol=1e-4)
