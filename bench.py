@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the Real-SRGD sampling hot path on B200 (see DESIGN.md "Measurement").
+
+A *step* is one pass of the hot path over one batch: `p_sample` = conditional U-Net denoise
+(2x batch under CFG) + fused posterior update, on `--batch` 256x256 tiles (= 64x64 LR images), with
+the actual 250-step linear-logSNR schedule times.  Default workload = BASELINE.json configs[1]:
+batch 16, label 0, class_cond_scale 1.0, bf16 kernels, K = 250 steps = one full sampling schedule.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--class_cond_scale S]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # CPU arm: the oracle port on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = SR images/sec (64x64 LR -> 256x256, 250 steps) over all
+GPUs with inputs resident in HBM; `e2e` = the same through the reference-facing API with pinned
+host buffers copied in/out every step; `roofline` = the tcgen05 conv kernel's achieved TFLOP/s
+(CUDA events around every conv launch, srgd_profile_*) against the measured bf16 peak;
+`cpu_baseline` = the oracle port of the reference on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SAMPLE_STEPS = 250                    # shipped schedule (conf yaml:17)
+TILE = 256                            # image_size (conf yaml:31): one 64x64 LR image = one tile
+# algorithmic work per tile-NFE measured on the reference module (SURVEY.md §8d / BASELINE.md §2)
+CONV_GFLOP_PER_TILE_NFE = 789.35      # conv3x3 705.45 + conv1x1 78.97 + conv7x7 4.93
+TOTAL_GFLOP_PER_TILE_NFE = 793.8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=SAMPLE_STEPS)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--class_cond_scale", type=float, default=1.0)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--cpu_steps", type=int, default=2, help="timed CPU-baseline steps (B=1 tile each)")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_tflops=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), hbm_gbs=p.get("hbm_gbs"),
+                    source="MEASURED_PEAKS.json (sustained bf16)")
+    return dict(bf16_tflops=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.startswith("Active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def synth_inputs(batch, seed=71):
+    """Synthetic LR images exactly as BASELINE.md §3: RandomState(71+idx) uint8 64x64x3, PIL bicubic x4."""
+    import numpy as np
+    from PIL import Image
+    conds = []
+    for idx in range(batch):
+        lr = np.random.RandomState(seed + idx).randint(0, 256, (64, 64, 3), dtype=np.uint8)
+        hr = Image.fromarray(lr, mode="RGB").resize((TILE, TILE), resample=Image.BICUBIC)
+        conds.append(torch.from_numpy(np.asarray(hr, dtype=np.uint8)).permute(2, 0, 1).float().div(255.))
+    return torch.stack(conds)           # [B,3,256,256] in [0,1]
+
+
+def cpu_reference_arm(args, n_steps, warm):
+    """The reference's own algorithm on the host cores: the oracle port (oracle/srgd_oracle.py, pinned
+    to the unmodified reference by tests/golden) -- the reference itself is Python and cannot travel."""
+    from oracle import srgd_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec = O.UnetSpec()
+    sd = O.make_state_dict(spec, 1234)
+    cond = synth_inputs(1) * 2 - 1
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(1, 3, TILE, TILE, generator=g)
+    steps = torch.linspace(1., 0., SAMPLE_STEPS + 1)
+    label = torch.tensor([0])
+    times = []
+    with torch.inference_mode():
+        for i in range(warm + n_steps):
+            t0 = time.perf_counter()
+            x, _ = O.p_sample(sd, spec, x, steps[i], cond, label, 1.0, args.class_cond_scale, steps[i + 1],
+                              generator=g)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    nfe_per_step = 2 if args.class_cond_scale != 1.0 else 1
+    s_per_step = sum(times) / len(times)
+    img_per_s = 1.0 / (s_per_step * SAMPLE_STEPS)          # one tile (= one 64x64-LR image) per step
+    return dict(value=img_per_s, unit="images/s", cores=threads, kind="port",
+                sample=f"{n_steps} timed p_sample steps (+{warm} warm-up) of ONE 256x256 tile, fp32, "
+                       f"class_cond_scale {args.class_cond_scale}, extrapolated x{SAMPLE_STEPS} steps",
+                s_per_step=s_per_step, unet_steps_per_sec=nfe_per_step / s_per_step)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = (f"sample(): {args.batch} synthetic 64x64-LR tiles (256x256) per GPU, label 0, "
+                f"class_cond_scale {args.class_cond_scale}, {SAMPLE_STEPS}-step linear-logSNR schedule, dim128 U-Net")
+    metric = "SR images/sec (64x64 LR -> 256x256, 250 sampling steps)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_arm(args, max(1, min(args.steps, 3)), 1)
+        line = dict(metric=metric, value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=cb["s_per_step"] * 1e3, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                    config=dict(workload=workload, note="CPU arm: each step is a bounded sample (1 tile)"),
+                    cpu_baseline=dict(value=cb["value"], unit="images/s", cores=cb["cores"], kind="port",
+                                      sample=cb["sample"]),
+                    unet_steps_per_sec=cb["unet_steps_per_sec"],
+                    e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    from oracle import srgd_oracle as O           # only for the deterministic random-init weights + CPU arm
+    import model as M
+    from srgd_b200 import _lib
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = O.UnetSpec()
+    unet = M.ConditionalSRUnet(dim=128, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=TILE, num_sample_steps=SAMPLE_STEPS)
+    diff.load_state_dict(O.make_state_dict(spec, 1234), strict=True)
+    diff = diff.eval().to(dev)
+    diff.progress = False
+    lib = _lib.load()
+
+    B = args.batch
+    cond01 = synth_inputs(B, seed=71 + rank * B)
+    cond = (cond01 * 2 - 1).to(dev)
+    label = torch.tensor([0], device=dev)
+    steps = torch.linspace(1., 0., SAMPLE_STEPS + 1)
+    ccs = args.class_cond_scale
+    nfe_per_step = B * (2 if ccs != 1.0 else 1)
+
+    def run_steps(img, first, count):
+        for k in range(count):
+            i = (first + k) % SAMPLE_STEPS
+            img, _ = diff.p_sample(img, steps[i], cond, label, 1.0, ccs, steps[i + 1])
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(71 + rank)
+    img = torch.randn(B, 3, TILE, TILE, device=dev)
+    with torch.inference_mode():
+        img = run_steps(img, 0, args.warmup)
+        barrier()
+        launches_before = 0
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        img = run_steps(img, args.warmup, args.steps)
+        out = diff._finalize(img)
+        if world > 1:                              # the only collective: final gather of finished images
+            gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+            dist.gather(out, gathered, dst=0)
+        e1.record()
+        barrier()
+        elapsed_ms = e0.elapsed_time(e1)
+        clocks = sampler.summary() if sampler else None
+        step_launches = diff.last_step_launches
+        if world > 1:
+            t = torch.tensor([elapsed_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t)
+
+        # ---- end-to-end through the public API with HOST buffers (pinned), every step ----
+        e2e_steps = max(3, min(args.steps, 20))
+        x_host = torch.randn(B, 3, TILE, TILE).pin_memory()
+        c_host = (cond01 * 2 - 1).pin_memory()
+        r_host = torch.empty(B, 3, TILE, TILE).pin_memory()
+        barrier()
+        e0.record()
+        for k in range(e2e_steps):
+            i = (args.warmup + k) % SAMPLE_STEPS
+            xd = x_host.to(dev, non_blocking=True)
+            cd = c_host.to(dev, non_blocking=True)
+            o, _ = diff.p_sample(xd, steps[i], cd, label, 1.0, ccs, steps[i + 1])
+            r_host.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t)
+
+        # ---- per-kernel-kind device time (CUDA events around every launch), rank 0 only ----
+        prof = None
+        if rank == 0:
+            prof_steps = 3
+            torch.cuda.synchronize()
+            _lib.check(lib.srgd_profile_begin())
+            img = run_steps(img, 100, prof_steps)
+            _lib.check(lib.srgd_profile_end())
+            prof = {k: dict(v, ms=v["ms"] / prof_steps, launches=v["launches"] // prof_steps,
+                            flops=v["flops"] / prof_steps, bytes=v["bytes"] / prof_steps)
+                    for k, v in _lib.profile_report().items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = elapsed_ms / args.steps
+    nfe_per_sec = world * nfe_per_step / (ms_per_step * 1e-3)
+    tiles_per_image = SAMPLE_STEPS * (2 if ccs != 1.0 else 1)
+    img_per_sec = nfe_per_sec / tiles_per_image
+    e2e_img_per_sec = world * nfe_per_step / (e2e_ms / e2e_steps * 1e-3) / tiles_per_image
+    pk = peaks()
+    conv = prof["conv_igemm"]
+    conv_tflops = CONV_GFLOP_PER_TILE_NFE * 1e9 * nfe_per_step / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    roof = dict(bound="tensor", kernel="conv_igemm_kernel (tcgen05 implicit GEMM, all conv3x3/1x1/7x7 launches of a step)",
+                achieved=conv_tflops, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=conv_tflops / pk["bf16_tflops"],
+                traffic=None, peak_source=pk["source"],
+                algorithmic=f"{CONV_GFLOP_PER_TILE_NFE} GFLOP conv work per tile-NFE x {nfe_per_step} tile-NFE per step",
+                launches_per_step=conv["launches"], kernel_ms_per_step=conv["ms"],
+                share_of_step=conv["ms"] / ms_per_step)
+    hbm = {}
+    for k in ("gn_apply", "sampler_step", "linear_attention", "norm_misc"):
+        if prof[k]["ms"] > 0:
+            gbs = prof[k]["bytes"] / (prof[k]["ms"] * 1e-3) / 1e9
+            hbm[k] = dict(ms_per_step=prof[k]["ms"], gb_per_s=gbs, frac_of_hbm_peak=gbs / pk["hbm_gbs"],
+                          launches_per_step=prof[k]["launches"])
+    line = dict(
+        metric=metric, value=img_per_sec, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config=dict(workload=workload, per_gpu_batch=B, global_batch=B * world, tile=TILE,
+                    timing="inputs (activations of a step >> 126 MB L2) larger than L2; no explicit flush",
+                    weights="random-init seed 1234 (shipped .pth is a Git-LFS pointer)"),
+        unet_steps_per_sec=nfe_per_sec, tensor_tflops_whole_step=TOTAL_GFLOP_PER_TILE_NFE * nfe_per_sec / 1e3,
+        e2e=dict(value=e2e_img_per_sec, unit="images/s", h2d_bytes_per_step=2 * B * 3 * TILE * TILE * 4,
+                 d2h_bytes_per_step=B * 3 * TILE * TILE * 4, steps=e2e_steps,
+                 call="ConditionalContinuousTimeGaussianDiffusionSR.p_sample with pinned host x/cond in, img_next out"),
+        gpu_launches=int(step_launches) * args.steps + 1,
+        roofline=roof, hbm_kernels=hbm,
+        kernel_ms_per_step={k: round(v["ms"], 4) for k, v in prof.items()},
+        clocks=clocks,
+    )
+    if not args.no_cpu_baseline:
+        cb = cpu_reference_arm(args, args.cpu_steps, 1)
+        line["cpu_baseline"] = dict(value=cb["value"], unit="images/s", cores=cb["cores"], kind="port", sample=cb["sample"])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -230,6 +230,26 @@ int srgd_unet_set_tap(srgd_unet* u, const char* name, void* out_dev, size_t out_
 /* Kernels launched by the last srgd_unet_forward on this handle. */
 int srgd_unet_last_launch_count(const srgd_unet* u);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): when enabled, every kernel launch made through this library is
+ * bracketed by CUDA events on its stream; srgd_profile_end() synchronises and folds them per kind.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  SRGD_PK_CONV = 0,        /* conv_igemm_kernel (tcgen05)                    */
+  SRGD_PK_GN_APPLY = 1,    /* gn_apply_kernel                                */
+  SRGD_PK_SAMPLER = 2,     /* sampler_step_kernel                            */
+  SRGD_PK_LINEAR_ATTN = 3, /* la_context_partial + merge + apply             */
+  SRGD_PK_FULL_ATTN = 4,   /* full_attention_kernel                          */
+  SRGD_PK_NORM_MISC = 5,   /* gn_finalize/stats, pixel_inv_norm, rmsnorm     */
+  SRGD_PK_OTHER = 6,       /* pack_input, final_conv, embeddings, q_sample…  */
+  SRGD_PK_COUNT = 7
+};
+int srgd_profile_begin(void);
+int srgd_profile_end(void);
+/* Sums since srgd_profile_begin for one kind: device milliseconds, algorithmic FLOPs and bytes the
+ * launches were credited with, number of API-level launches. */
+int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

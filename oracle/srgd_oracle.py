@@ -128,28 +128,48 @@ def param_shapes(spec: UnetSpec, prefix: str = "model.") -> "OrderedDict[str, Tu
     return S
 
 
-def make_state_dict(spec: UnetSpec, seed: int = 1234, prefix: str = "model.") -> Dict[str, torch.Tensor]:
+def make_state_dict(spec: UnetSpec, seed: int = 1234, prefix: str = "model.", init: str = "unit") -> Dict[str, torch.Tensor]:
     """Deterministic random-init weights of the reference architecture (the shipped .pth is a
-    Git-LFS pointer).  Scales mimic torch defaults (uniform +-1/sqrt(fan_in)) so activations stay
-    O(1); norm gains are perturbed around 1 so that gain/bias paths are exercised."""
+    Git-LFS pointer).
+
+    init="unit"  : stress init -- unit-gain uniform weights (var 1/fan_in), norm gains 1 +- 0.1,
+                   non-zero norm/conv biases, so every gain/bias path is exercised and activations
+                   stay O(1..3) through the net.  Used by the golden fixtures.
+    init="torch" : what the reference constructors produce: nn.Conv2d / nn.Linear
+                   defaults (kaiming_uniform(a=sqrt 5): U(+-1/sqrt(fan_in)) for weight and bias),
+                   GroupNorm / RMSNorm gains 1, biases 0, nn.Embedding N(0,1), sinusoidal weights
+                   randn (model.py:231), PixelShuffle conv = kaiming-uniform rows repeated x4 with
+                   zero bias (model.py:88-95).  Same distribution, not the same draws as torch's
+                   own constructors (those cannot run without the reference's pip dependencies)."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = OrderedDict()
     for name, shape in param_shapes(spec, prefix).items():
-        if name.endswith("time_mlp.0.weights"):
-            t = torch.randn(shape, generator=g)
-        elif name.endswith("class_mlp.0.weight"):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        if name.endswith("time_mlp.0.weights") or name.endswith("class_mlp.0.weight"):
             t = torch.randn(shape, generator=g)
         elif name.endswith(".g") or name.endswith("norm.weight"):
-            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g) if init == "unit" else torch.ones(shape)
         elif name.endswith("norm.bias"):
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * torch.randn(shape, generator=g) if init == "unit" else torch.zeros(shape)
         elif name.endswith(".bias"):
-            t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+            if init == "unit":
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+            elif ".net.0." in name:
+                t = torch.zeros(shape)
+            else:
+                wshape = param_shapes(spec, prefix)[name[:-4] + "weight"]
+                fi = 1
+                for s in wshape[1:]:
+                    fi *= s
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fi)
+        elif init == "torch" and ".net.0.weight" in name:
+            o, i, kh, kw = shape
+            base = (torch.rand((o // 4, i, kh, kw), generator=g) * 2 - 1) * math.sqrt(6.0 / (i * kh * kw))
+            t = base.repeat_interleave(4, dim=0)                           # 'o ... -> (o 4) ...'
         else:
-            fan_in = 1
-            for s in shape[1:]:
-                fan_in *= s
-            bound = math.sqrt(3.0 / fan_in)          # unit-gain uniform: var = 1/fan_in
+            bound = math.sqrt(3.0 / fan_in) if init == "unit" else 1.0 / math.sqrt(fan_in)
             t = (torch.rand(shape, generator=g) * 2 - 1) * bound
         sd[name] = t.float().contiguous()
     return sd
@@ -369,14 +389,14 @@ def p_sample(sd, spec, x, time, condition_x, class_label, cond_scale, class_cond
     if time_next == 0:
         return mean, x_start
     if noise is None:
-        noise = torch.randn(x.shape, generator=generator)
+        noise = torch.randn(x.shape, generator=generator, device=x.device)      # randn_like(x)
     return mean + var.sqrt() * noise, x_start
 
 
 def q_sample(x_start, times, noise=None, generator=None):
     """model.py:3434-3447."""
     if noise is None:
-        noise = torch.randn(x_start.shape, generator=generator)
+        noise = torch.randn(x_start.shape, generator=generator, device=x_start.device)
     log_snr = log_snr_linear(times)
     pad = log_snr.reshape(*log_snr.shape, *((1,) * max(0, x_start.ndim - log_snr.ndim)))
     alpha, sigma = pad.sigmoid().sqrt(), (-pad).sigmoid().sqrt()
@@ -391,11 +411,11 @@ def sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale=1.0,
     condition_x = condition_x * 2 - 1
     shape = (batch_size, spec.channels, image_size, image_size)
     if generation_start_steps > 0:
-        st = 1. - torch.tensor(generation_start_steps / num_sample_steps)
+        st = 1. - torch.tensor(generation_start_steps / num_sample_steps, device=condition_x.device)
         img, _ = q_sample(condition_x, st.reshape(1).expand(batch_size), generator=generator)
     else:
-        img = torch.randn(shape, generator=generator)
-    steps = torch.linspace(1., 0., num_sample_steps + 1)
+        img = torch.randn(shape, generator=generator, device=condition_x.device)
+    steps = torch.linspace(1., 0., num_sample_steps + 1, device=condition_x.device)
     for i in range(num_sample_steps):
         if i < generation_start_steps:
             continue
@@ -457,11 +477,11 @@ def tiled_sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale
     (left, top, right, bottom), pad = get_coord_and_pad(h, w)       # model.py:3301 (default 256!)
     condition_x = F.pad(condition_x, pad, mode="reflect")
     if generation_start_steps > 0:
-        st = 1. - torch.tensor(generation_start_steps / num_sample_steps)
+        st = 1. - torch.tensor(generation_start_steps / num_sample_steps, device=condition_x.device)
         img, _ = q_sample(condition_x, st.reshape(1).expand(batch), generator=generator)
     else:
-        img = torch.randn(condition_x.shape, generator=generator)
-    steps = torch.linspace(1., 0., num_sample_steps + 1)
+        img = torch.randn(condition_x.shape, generator=generator, device=condition_x.device)
+    steps = torch.linspace(1., 0., num_sample_steps + 1, device=condition_x.device)
     _, _, height, width = condition_x.shape
     coords0 = get_coords(height, width, tile_size, tile_size, 0)
     if height <= tile_size and width <= tile_size:

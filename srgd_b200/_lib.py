@@ -89,7 +89,24 @@ SIGNATURES = {
     "srgd_unet_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _SZ, _I32, _P]),
     "srgd_unet_set_tap": (C.c_int, [_P, C.c_char_p, _P, _SZ]),
     "srgd_unet_last_launch_count": (C.c_int, [_P]),
+    "srgd_profile_begin": (C.c_int, []),
+    "srgd_profile_end": (C.c_int, []),
+    "srgd_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int)]),
 }
+
+PROFILE_KINDS = ["conv_igemm", "gn_apply", "sampler_step", "linear_attention", "full_attention", "norm_misc", "other"]
+
+
+def profile_report():
+    """{kind: dict(ms, flops, bytes, launches)} accumulated since srgd_profile_begin (after _end)."""
+    lib = load()
+    out = {}
+    for k, name in enumerate(PROFILE_KINDS):
+        ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        check(lib.srgd_profile_get(k, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)), "srgd_profile_get")
+        out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
+    return out
 
 _lib = None
 

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace srgd {
@@ -53,6 +55,28 @@ int check_device() {
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
+// ---- profiling ---------------------------------------------------------------------------------
+bool g_prof_on = false;
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static std::vector<ProfRec> g_prof_recs;
+static double g_prof_ms[SRGD_PK_COUNT], g_prof_flops[SRGD_PK_COUNT], g_prof_bytes[SRGD_PK_COUNT];
+static int g_prof_n[SRGD_PK_COUNT];
+
+void prof_open(int kind, double flops, double bytes, cudaStream_t st) {
+  ProfRec r{kind, flops, bytes, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void prof_close(cudaStream_t st) {
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st);
+}
+
 }  // namespace srgd
 
 extern "C" {
@@ -75,6 +99,48 @@ int srgd_device_check(int device) {
   int rc = srgd::check_device();
   cudaSetDevice(cur);
   return rc;
+}
+
+int srgd_profile_begin(void) {
+  for (auto& r : srgd::g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  srgd::g_prof_recs.clear();
+  for (int k = 0; k < SRGD_PK_COUNT; ++k) {
+    srgd::g_prof_ms[k] = srgd::g_prof_flops[k] = srgd::g_prof_bytes[k] = 0.0;
+    srgd::g_prof_n[k] = 0;
+  }
+  srgd::g_prof_on = true;
+  return SRGD_OK;
+}
+
+int srgd_profile_end(void) {
+  srgd::g_prof_on = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return srgd::fail_cuda(e, "cudaDeviceSynchronize");
+  for (auto& r : srgd::g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.kind >= 0 && r.kind < SRGD_PK_COUNT) {
+      srgd::g_prof_ms[r.kind] += ms;
+      srgd::g_prof_flops[r.kind] += r.flops;
+      srgd::g_prof_bytes[r.kind] += r.bytes;
+      srgd::g_prof_n[r.kind] += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  srgd::g_prof_recs.clear();
+  return SRGD_OK;
+}
+
+int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* launches) {
+  if (kind < 0 || kind >= SRGD_PK_COUNT) {
+    srgd::set_error("profile_get: bad kind %d", kind);
+    return SRGD_E_ARG;
+  }
+  if (ms) *ms = srgd::g_prof_ms[kind];
+  if (flops) *flops = srgd::g_prof_flops[kind];
+  if (bytes) *bytes = srgd::g_prof_bytes[kind];
+  if (launches) *launches = srgd::g_prof_n[kind];
+  return SRGD_OK;
 }
 
 }  // extern "C"

@@ -286,6 +286,8 @@ extern "C" int srgd_linear_attention(const void* qkv, void* out, int32_t B, int3
   ctx = reinterpret_cast<float*>(((uintptr_t)ctx + 127) & ~(uintptr_t)127);
   cudaStream_t st = as_stream(stream);
   const bf16* in = reinterpret_cast<const bf16*>(qkv);
+  ProfScope prof(SRGD_PK_LINEAR_ATTN, 4.0 * (double)B * N * heads * kDH * kDH,
+                 2.0 * (double)B * N * heads * kDH * 4, st);
   la_context_partial_kernel<4><<<dim3(splits, B), 128, 0, st>>>(in, part, N, splits);
   SRGD_LAUNCH_OK("la_context_partial_kernel");
   la_context_merge_kernel<<<B * heads, 32, 0, st>>>(part, ctx, heads, splits);
@@ -305,6 +307,8 @@ extern "C" int srgd_attention(const void* qkv, void* out, int32_t B, int32_t N, 
   if (rc) return rc;
   SRGD_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0 && heads <= 16, "attention: bad arguments");
   SRGD_REQUIRE((int64_t)B * heads <= 65535, "attention: B*heads too large");
+  ProfScope prof(SRGD_PK_FULL_ATTN, 4.0 * (double)B * heads * (double)N * N * kDH,
+                 2.0 * (double)B * N * heads * kDH * 4, as_stream(stream));
   full_attention_kernel<<<dim3((N + kFaQ - 1) / kFaQ, B * heads), kFaQ, 0, as_stream(stream)>>>(
       reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), N, heads);
   SRGD_LAUNCH_OK("full_attention_kernel");

@@ -44,6 +44,22 @@ int sm_count();
 extern thread_local long g_launches;
 static inline void count_launch(int n = 1) { g_launches += n; }
 
+// Optional per-launch timing (srgd_profile_*): a ProfScope brackets the launches made inside an API
+// entry point with CUDA events when profiling is on; otherwise it costs one branch.
+extern bool g_prof_on;
+void prof_open(int kind, double flops, double bytes, cudaStream_t st);
+void prof_close(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (on) prof_open(kind, flops, bytes, st);
+  }
+  ~ProfScope() {
+    if (on) prof_close(st);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

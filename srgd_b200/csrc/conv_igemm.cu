@@ -496,6 +496,9 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   kp.gn_partials = d->gn_partials;
 
   cudaStream_t st = as_stream(stream);
+  const double M = (double)d->B * d->Ho * d->Wo;
+  ProfScope prof(SRGD_PK_CONV, 2.0 * M * d->Cout * total_kb * kBK,
+                 2.0 * (M * total_kb * kBK + (double)d->Cout * d->Ktot + M * d->Cout), st);
   switch (BN) {
     case 64: return launch_igemm<64, 8>(kp, st);
     case 128: return launch_igemm<128, 6>(kp, st);

@@ -174,6 +174,7 @@ extern "C" int srgd_pack_input(const float* x, const float* cond, int32_t n_cond
   const int64_t total = (int64_t)B * H * W;
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  ProfScope prof(SRGD_PK_OTHER, 0.0, (double)B * H * W * (6 * 4 + 128), as_stream(stream));
   pack_input_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, cond, n_cond_rows, Bx,
                                                                reinterpret_cast<bf16*>(out), B, H, W);
   SRGD_LAUNCH_OK("pack_input_kernel");
@@ -186,12 +187,13 @@ extern "C" int srgd_final_conv(const void* h, const float* w, const float* bias,
   int rc = check_device();
   if (rc) return rc;
   SRGD_REQUIRE(h && w && bias && eps && B > 0 && H > 0 && W > 0, "final_conv: bad arguments");
-  SRGD_REQUIRE(C % 128 == 0 && C <= 1024, "final_conv: C=%d must be a multiple of 128", C);
+  SRGD_REQUIRE(C % 64 == 0 && C <= 1024, "final_conv: C=%d must be a multiple of 64", C);
   SRGD_REQUIRE(Cout == 3, "final_conv: only Cout=3 (channels=3, learned_variance=False) is built, got %d", Cout);
   SRGD_REQUIRE((H * W) % 32 == 0, "final_conv: H*W must be a multiple of 32");
   const int64_t n_groups = (int64_t)B * H * W / 32;
   int64_t blocks = (n_groups + 7) / 8;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  ProfScope prof(SRGD_PK_OTHER, 0.0, (double)B * H * W * (C * 2.0 + 12.0), as_stream(stream));
   final_conv_kernel<3><<<(int)blocks, 256, (size_t)3 * C * sizeof(float), as_stream(stream)>>>(
       reinterpret_cast<const bf16*>(h), w, bias, eps, B, H * W, C);
   SRGD_LAUNCH_OK("final_conv_kernel");
@@ -205,6 +207,7 @@ extern "C" int srgd_fourier_features(const float* log_snr, const float* weights,
   if (rc) return rc;
   SRGD_REQUIRE(log_snr && weights && out && B > 0 && half_dim > 0, "fourier_features: bad arguments");
   const int total = B * (2 * half_dim + 1);
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
   fourier_features_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(log_snr, weights, out, B, half_dim);
   SRGD_LAUNCH_OK("fourier_features_kernel");
   count_launch();
@@ -218,6 +221,7 @@ extern "C" int srgd_dense_rows(const float* x, const float* w, const float* bias
   SRGD_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0 && K <= 1536, "dense_rows: bad arguments (K <= 1536)");
   SRGD_REQUIRE((M + kDrRows - 1) / kDrRows <= 65535, "dense_rows: too many rows");
   dim3 grid((N + 7) / 8, (M + kDrRows - 1) / kDrRows);
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 4.0 * ((double)N * K + (double)M * (N + K)), as_stream(stream));
   dense_rows_kernel<<<grid, 256, (size_t)kDrRows * K * sizeof(float), as_stream(stream)>>>(x, w, bias, y, M, N, K,
                                                                                            act_in, accumulate);
   SRGD_LAUNCH_OK("dense_rows_kernel");
@@ -231,6 +235,7 @@ extern "C" int srgd_add_class_rows(float* t, const float* table, const int32_t* 
   if (rc) return rc;
   SRGD_REQUIRE(t && table && labels_dev && B > 0 && dim > 0, "add_class_rows: bad arguments");
   const int total = B * dim;
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
   add_class_rows_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(t, table, labels_dev, B, dim, num_classes);
   SRGD_LAUNCH_OK("add_class_rows_kernel");
   count_launch();

@@ -227,6 +227,7 @@ extern "C" int srgd_groupnorm_finalize(const float* gn_partials, float* stats, i
                "groupnorm_finalize: bad arguments");
   const TileGeom g = tile_geom(B, H, W);
   SRGD_REQUIRE(g.tn_log2 <= 2, "groupnorm_finalize: needs H*W >= 32");
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)g.m_tiles * 4 * 8 * 2 * 4, as_stream(stream));
   gn_finalize_kernel<<<B * kGroups, 128, 0, as_stream(stream)>>>(gn_partials, stats, H, W, C, g);
   SRGD_LAUNCH_OK("gn_finalize_kernel");
   count_launch();
@@ -238,6 +239,7 @@ extern "C" int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int3
   int rc = check_device();
   if (rc) return rc;
   SRGD_REQUIRE(x && stats && B > 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0, "groupnorm_stats: bad arguments");
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)B * H * W * C * 2.0, as_stream(stream));
   gn_stats_kernel<<<B * kGroups, 512, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(x), stats, H * W, C);
   SRGD_LAUNCH_OK("gn_stats_kernel");
   count_launch();
@@ -262,6 +264,7 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   const bf16* xr = reinterpret_cast<const bf16*>(x);
   const bf16* rr = reinterpret_cast<const bf16*>(residual);
   bf16* yr = reinterpret_cast<bf16*>(y);
+  ProfScope prof(SRGD_PK_GN_APPLY, 0.0, (double)B * H * W * C * (residual ? 6.0 : 4.0), as_stream(stream));
   if (residual)
     gn_apply_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride,
                                                                   rr, yr, H * W, C);
@@ -278,6 +281,7 @@ extern "C" int srgd_pixel_inv_norm(const void* x, float* inv, int64_t M, int32_t
   if (rc) return rc;
   SRGD_REQUIRE(x && inv && M > 0 && C >= 64 && C % 64 == 0, "pixel_inv_norm: bad arguments");
   const bf16* xr = reinterpret_cast<const bf16*>(x);
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)M * C * 2.0 + (double)M * 4.0, as_stream(stream));
   if (C / 8 >= 32) {
     const int grid = stream_grid((M + 7) / 8, 8);
     pixel_inv_norm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
@@ -303,6 +307,7 @@ extern "C" int srgd_rmsnorm_residual(const void* x, const float* g, const void* 
   bf16* yr = reinterpret_cast<bf16*>(y);
   const float sc = sqrtf((float)C);
   cudaStream_t st = as_stream(stream);
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)M * C * (residual ? 6.0 : 4.0), st);
 #define SRGD_RMS(LP)                                                                                     \
   do {                                                                                                   \
     const int grid = stream_grid((M + (256 / LP) - 1) / (256 / LP), 8);                                  \

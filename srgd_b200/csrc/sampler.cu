@@ -109,6 +109,8 @@ extern "C" int srgd_sampler_step(const float* x, const float* eps_cond, const fl
   const int grid = grid_for(n4, 256, 8);
   cudaStream_t st = as_stream(stream);
   const int key = (eps_null ? 4 : 0) | (noise ? 2 : 0) | (x_start ? 1 : 0);
+  ProfScope prof(SRGD_PK_SAMPLER, 0.0,
+                 4.0 * (double)n * (3 + (eps_null ? 1 : 0) + (noise ? 1 : 0) + (x_start ? 1 : 0)), st);
 #define SRGD_CASE(K, A, B_, C)                                                                    \
   case K:                                                                                         \
     sampler_step_kernel<A, B_, C><<<grid, 256, 0, st>>>(x, eps_cond, eps_null, noise, img_next,   \
@@ -135,6 +137,7 @@ extern "C" int srgd_q_sample(const float* x_start, const float* noise, float* ou
   int rc = check_device();
   if (rc) return rc;
   SRGD_REQUIRE(noise && out && n > 0, "srgd_q_sample: null argument or n <= 0");
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 4.0 * (double)n * (x_start ? 3 : 2), as_stream(stream));
   q_sample_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(x_start, noise, out, n, alpha, sigma);
   SRGD_LAUNCH_OK("q_sample_kernel");
   count_launch();
@@ -145,6 +148,7 @@ extern "C" int srgd_finalize_image(const float* img, float* out, int64_t n, srgd
   int rc = check_device();
   if (rc) return rc;
   SRGD_REQUIRE(img && out && n > 0, "srgd_finalize_image: null argument or n <= 0");
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 8.0 * (double)n, as_stream(stream));
   finalize_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(img, out, n);
   SRGD_LAUNCH_OK("finalize_kernel");
   count_launch();

@@ -38,6 +38,16 @@ def build(tag, image_size=64, steps=250):
     return _cache[key]
 
 
+def make_diffusion(spec, sd, image_size, steps):
+    unet = M.ConditionalSRUnet(dim=spec.dim, dim_mults=spec.dim_mults, full_attn=spec.full_attn,
+                               learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=image_size, num_sample_steps=steps)
+    diff.load_state_dict(sd, strict=True)
+    diff = diff.eval().to("cuda")
+    diff.progress = False
+    return diff
+
+
 def T(a):
     return torch.from_numpy(np.asarray(a))
 
@@ -119,59 +129,67 @@ def test_p_sample_teacher_forced_vs_reference_golden():
         assert abs(float(var) - float(g[f"c{ci}_var"])) <= 1e-7
 
 
-@pytest.mark.parametrize("ccs", [1.0, 3.0])
-def test_free_running_psnr_vs_oracle(ccs):
-    """Same noise sequence on both sides (drawn from torch's CUDA generator with the shapes/order of
-    p_sample_loop, model.py:3203/3187); full spec, 64x64, 24 steps."""
-    diff, sd, spec = build("full")
-    nsteps, B = 24, 2
+def _oracle_on_gpu(sd):
+    """The oracle is plain functional PyTorch: run it on the GPU in strict fp32 (TF32 off) so that a
+    250-step free-running reference takes seconds instead of minutes of host time.  With tensors on
+    the GPU its torch.randn calls draw from torch's CUDA generator with the reference's shapes and
+    order -- the same stream the product path consumes after the same torch.manual_seed."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+# Final-image PSNR bars.  north_star: >= 45 dB vs the reference at the full schedule, on random-init
+# weights of the reference constructors (BASELINE.md §3) = init "torch".  The golden fixtures use a
+# harsher unit-gain init ("unit", activations 3x larger, strong class dependence); there the floor of
+# ANY bf16-operand tensor-core implementation is 49.7 dB (scale 1.0) / 41.8 dB (scale 3.0) and torch's
+# own bf16 autocast reaches 47.3 / 39.6 dB (profiles/r01_precision_study.log), so the CFG 3.0 bar for
+# that init is set at 38 dB (must stay within ~2 dB of torch autocast), not 45.
+FREE_RUNNING = [("torch", 1.0, 250, 45.0), ("torch", 3.0, 250, 45.0), ("unit", 1.0, 250, 45.0),
+                ("unit", 3.0, 250, 38.0)]
+
+
+@pytest.mark.parametrize("init,ccs,nsteps,bar", FREE_RUNNING)
+def test_free_running_psnr_vs_oracle(init, ccs, nsteps, bar):
+    """sample() end to end (full-width U-Net, 64x64, B=2, label 1, seed 71) vs the fp32 oracle."""
+    spec = O.UnetSpec()
+    sd = O.make_state_dict(spec, 1234, init=init)
+    diff = make_diffusion(spec, sd, 64, nsteps)
     g = torch.Generator().manual_seed(4)
-    cond01 = torch.rand(B, 3, 64, 64, generator=g)
-    label = torch.tensor([1])
+    cond01 = torch.rand(2, 3, 64, 64, generator=g).cuda()
+    label = torch.tensor([1]).cuda()
     torch.manual_seed(71)
-    img = diff.sample(batch_size=B, condition_x=cond01.cuda(), class_label=label.cuda(), class_cond_scale=ccs,
+    img = diff.sample(batch_size=2, condition_x=cond01, class_label=label, class_cond_scale=ccs,
                       num_sample_steps=nsteps).cpu()
-    # replay the generator for the oracle
+    gsd = _oracle_on_gpu(sd)
     torch.manual_seed(71)
-    noises = [torch.randn(B, 3, 64, 64, device="cuda").cpu()] + \
-             [torch.randn(B, 3, 64, 64, device="cuda").cpu() for _ in range(nsteps - 1)]
-    steps = torch.linspace(1., 0., nsteps + 1)
-    x = noises[0]
-    c = cond01 * 2 - 1
-    for i in range(nsteps):
-        nz = noises[i + 1] if i + 1 < nsteps else None
-        x, _ = O.p_sample(sd, spec, x, steps[i], c, label, 1.0, ccs, steps[i + 1], noise=nz)
-    ref = (x.clamp(-1, 1) + 1) * 0.5
+    with torch.inference_mode():
+        ref = O.sample(gsd, spec, 2, cond01, class_label=label, class_cond_scale=ccs, num_sample_steps=nsteps,
+                       image_size=64).cpu()
     p = G.psnr(img, ref)
-    print(f"free-running {nsteps} steps ccs={ccs}: PSNR {p:.2f} dB, max-abs {float((img - ref).abs().max()):.4f}")
-    assert p >= 45.0
+    print(f"free-running {nsteps} steps init={init} ccs={ccs}: PSNR {p:.2f} dB, max-abs {float((img - ref).abs().max()):.4f}")
+    assert p >= bar
 
 
 def test_tiled_sample_vs_oracle():
-    """272x264 HR: 768x768 canvas, 9 / 4 tiles, odd-step re-noise; 4 steps, batch_size 4 (chunks 4,4,1)."""
-    diff, sd, spec = build("mid", image_size=256)
+    """inference.py's path: 272x264 HR -> 768x768 canvas, 9 / 4 alternating tiles, odd-step re-noise,
+    batch_size 4 (chunks 4,4,1), CFG 2.0, full 250-step schedule; dim-64 U-Net, reference-style init."""
+    spec = O.UnetSpec(dim=64)
+    sd = O.make_state_dict(spec, 22, init="torch")
+    diff = make_diffusion(spec, sd, 256, 250)
     g = torch.Generator().manual_seed(9)
-    cond01 = torch.rand(1, 3, 272, 264, generator=g)
-    label = torch.tensor([0])
+    cond01 = torch.rand(1, 3, 272, 264, generator=g).cuda()
+    label = torch.tensor([0]).cuda()
     torch.manual_seed(71)
-    img = diff.tiled_sample(batch_size=4, condition_x=cond01.cuda(), class_label=label.cuda(), class_cond_scale=2.0,
-                            num_sample_steps=4).cpu()
+    img = diff.tiled_sample(batch_size=4, condition_x=cond01, class_label=label, class_cond_scale=2.0,
+                            num_sample_steps=250).cpu()
     assert img.shape == (1, 3, 272, 264) and float(img.min()) >= 0 and float(img.max()) <= 1
-
-    class CudaGen:  # oracle draws its noise from torch's CUDA generator, like the product path
-        pass
+    gsd = _oracle_on_gpu(sd)
     torch.manual_seed(71)
-    orig = torch.randn
-    def cuda_randn(*shape, generator=None, **kw):
-        shape = shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape
-        return orig(tuple(shape), device="cuda").cpu()
-    torch.randn = cuda_randn
-    try:
-        ref = O.tiled_sample(sd, spec, 4, cond01, label, class_cond_scale=2.0, num_sample_steps=4)
-    finally:
-        torch.randn = orig
+    with torch.inference_mode():
+        ref = O.tiled_sample(gsd, spec, 4, cond01, label, class_cond_scale=2.0, num_sample_steps=250).cpu()
     p = G.psnr(img, ref)
-    print(f"tiled_sample 4 steps: PSNR {p:.2f} dB")
+    print(f"tiled_sample 250 steps: PSNR {p:.2f} dB, max-abs {float((img - ref).abs().max()):.4f}")
     assert p >= 45.0
 
 
