@@ -19,6 +19,7 @@
 //                                  residual, bf16 store in NHWC or pixel-shuffled NHWC)
 // The double-buffered accumulator lets the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -252,7 +253,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          for (int j = 0; j < 32; j += 2) silu2(f[j], f[j + 1]);
         }
         if (valid && nc < p.Cout) {
           int64_t off;
@@ -294,6 +295,243 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         }
         __syncwarp();
       }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Channels-as-M" variant for Cout tiles of exactly 128 (Cout = 128, 384):
+//   D^T[M = 128 output channels, N = 256 pixels] = W_tile[128, K] * Act[256 pixels, K]^T
+// With pixels as M and N = 128 the tensor core reads A (4 KiB) + B (4 KiB) of shared memory per
+// 64-clock K=16 instruction = 128 B/clk, the whole shared-memory bandwidth, while TMA is writing the
+// same memory: measured 650 TFLOP/s on the 128->128 convs at 256^2 (profiles/r01_launches_v1.md).
+// Making the two 128-pixel sub-tiles the N = 256 operand drops that to 96 B/clk (like the
+// Cout >= 256 tiles, which run at ~1.4 PFLOP/s) and halves the weight traffic per pixel.
+// The accumulator comes out channel-major (TMEM lane = channel), so the epilogue transposes
+// through a 32 KiB shared-memory staging tile and writes fully coalesced 256-byte NHWC rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTN = 256;                     // pixels per tile (two sub-tiles of 128)
+constexpr int kTStages = 4;
+struct ConvSmemT {
+  static constexpr int kWBytes = 128 * kBK * 2;            // weights: A operand, 16 KiB
+  static constexpr int kXBytes = kTN * kBK * 2;            // activations: B operand, 32 KiB
+  static constexpr int kStageBytes = kWBytes + kXBytes;    // 48 KiB
+  static constexpr int kStagingOffset = kTStages * kStageBytes;
+  static constexpr int kStagingBytes = 128 * 128 * 2;      // [128 pixels][128 ch] bf16
+  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kTStages + 4) * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_constant__ ConvKernelParams p) {
+  using L = ConvSmemT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  bf16* staging = reinterpret_cast<bf16*>(smem + L::kStagingOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kTStages;
+  uint64_t* tfull_bar = empty_bar + kTStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;                      // 2 accumulator stages x 256 pixel columns
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_src; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
+    ptx::prefetch_tmap(&p.w_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+  const int tn_log2 = 7 - p.tw_log2 - p.th_log2;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  // tile -> (pair of pixel sub-tiles, 128-channel slab); n fastest so concurrent CTAs share activations
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int pair = tile / p.n_tiles;
+      int x0[2], y0[2], b0[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int st = pair * 2 + s;                       // may be == m_tiles (odd count): all OOB -> zeros
+        x0[s] = (st % p.tiles_x) << p.tw_log2;
+        y0[s] = ((st / p.tiles_x) % p.tiles_y) << p.th_log2;
+        b0[s] = (st / tiles_xy) << tn_log2;
+      }
+      for (int ph = 0; ph < p.n_phase; ++ph) {
+        const CUtensorMap* amap = &p.a_maps[p.ph_src[ph]];
+        const int dx = p.ph_dx[ph], dy = p.ph_dy[ph];
+        const int kblk0 = p.ph_kblk[ph];
+        const int ncb = p.ph_cblocks[ph];
+        for (int cb = 0; cb < ncb; ++cb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* w_dst = smem + stage * L::kStageBytes;
+          uint8_t* x_dst = w_dst + L::kWBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::tma_load_2d(w_dst, &p.w_map, &full_bar[stage], (kblk0 + cb) * kBK, n_tile * 128);
+          ptx::tma_load_4d(x_dst, amap, &full_bar[stage], cb * kBK, x0[0] + dx, y0[0] + dy, b0[0]);
+          ptx::tma_load_4d(x_dst + kABytes, amap, &full_bar[stage], cb * kBK, x0[1] + dx, y0[1] + dy, b0[1]);
+          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, kTN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kTN;
+      for (int kb = 0; kb < p.total_kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t w_addr = ptx::smem_u32(smem + stage * L::kStageBytes);
+        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(w_addr);                 // weights  [128 ch][64 k]
+        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(w_addr + L::kWBytes);    // pixels   [256 px][64 k]
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&empty_bar[stage]);
+        if (kb == p.total_kblocks - 1) ptx::umma_commit(&tfull_bar[acc]);
+        if (++stage == kTStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;                                // TMEM lane quarter = 32 output channels
+    const int et = threadIdx.x - 128;                      // 0..127 within the epilogue warps
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int pair = tile / p.n_tiles;
+      const int ch = n_tile * 128 + q * 32 + lane;         // this thread's output channel
+      const float bias = (p.bias != nullptr) ? __ldg(p.bias + ch) : 0.f;
+
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTN;
+
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        const int st = pair * 2 + s;
+        const int tx = st % p.tiles_x, ty = (st / p.tiles_x) % p.tiles_y, tb = st / tiles_xy;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {                      // 32-pixel column chunk = pixel quarter c
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_row + s * 128 + c * 32, v);
+          // lane j describes pixel column j of this chunk
+          const int r = c * 32 + lane;
+          const int px = (tx << p.tw_log2) + (r & (tw - 1));
+          const int py = (ty << p.th_log2) + ((r >> p.tw_log2) & (th - 1));
+          const int pb = (tb << tn_log2) + (r >> (p.tw_log2 + p.th_log2));
+          const bool pvalid = (px < p.Wo) && (py < p.Ho) && (pb < p.B);
+          const uint32_t vmask = __ballot_sync(0xffffffffu, pvalid);
+          float rs_lane = 1.0f;
+          if (p.row_scale != nullptr && pvalid) rs_lane = p.row_scale[((int64_t)pb * p.Ho + py) * p.Wo + px];
+          ptx::tmem_ld_wait();
+          float f[32];
+          if (p.row_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * __shfl_sync(0xffffffffu, rs_lane, j) + bias;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias;
+          }
+          if (p.gn_partials != nullptr) {
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = ((vmask >> j) & 1u) ? f[j] : 0.f;
+              sum += t;
+              sq += t * t;
+            }
+            // reduce over the lanes of one GroupNorm group (16 or 32 channels)
+            if (p.group_size >= 32) {
+              sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
+            const int lanes_per_group = p.group_size >= 32 ? 32 : 16;
+            if ((lane & (lanes_per_group - 1)) == 0 && st < p.m_tiles) {
+              const int g = ch / p.group_size;
+              float* dst = p.gn_partials + (((int64_t)st * 4 + c) * 8 + g) * 2;
+              dst[0] = sum;
+              dst[1] = sq;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) silu2(f[j], f[j + 1]);
+          }
+          // transpose: staging[pixel][channel]; one 64-byte row segment per store instruction
+          bf16* col = staging + (c * 32) * 128 + q * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) col[j * 128] = __float2bfloat16(f[j]);
+        }
+        if (s == 1) {
+          // whole accumulator has been read: release it before the (slower) copy-out
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+        // all four warps have filled the staging tile -> coalesced copy-out of 128 rows x 256 B
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int vec = et + i * 128;                    // 2048 vectors of 16 B
+          const int r = vec >> 4, part = vec & 15;
+          const int px = (tx << p.tw_log2) + (r & (tw - 1));
+          const int py = (ty << p.th_log2) + ((r >> p.tw_log2) & (th - 1));
+          const int pb = (tb << tn_log2) + (r >> (p.tw_log2 + p.th_log2));
+          if ((px < p.Wo) && (py < p.Ho) && (pb < p.B)) {
+            const uint4 val = *reinterpret_cast<const uint4*>(staging + r * 128 + part * 8);
+            bf16* dst = p.out + (((int64_t)pb * p.Ho + py) * p.Wo + px) * p.Cout + n_tile * 128 + part * 8;
+            st_stream(dst, val);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // staging is free again
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -408,6 +646,20 @@ static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
   return SRGD_OK;
 }
 
+static int launch_igemm_t(const ConvKernelParams& kp, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ConvSmemT::kTotal));
+    configured = true;
+  }
+  int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
+  conv_igemm_t_kernel<<<grid, kThreads, ConvSmemT::kTotal, st>>>(kp);
+  SRGD_LAUNCH_OK("conv_igemm_t_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
 }  // namespace srgd
 
 using namespace srgd;
@@ -429,6 +681,11 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   }
   const TileGeom g = tile_geom(d->B, d->Ho, d->Wo);
 
+  // channels-as-M variant for 128-wide Cout slabs (see conv_igemm_t_kernel)
+  const char* force = getenv("SRGD_CONV_VARIANT");         // test knob: "n" = pixels-as-M only
+  const bool swapped = d->Cout % 128 == 0 && d->Cout % 256 != 0 && d->residual == nullptr &&
+                       d->out_mode == SRGD_OUT_BF16_NHWC && (d->gn_partials == nullptr || d->Cout / 8 <= 32) &&
+                       !(force != nullptr && force[0] == 'n');
   // pick the N tile: widest that divides Cout, but keep enough tiles to fill the SMs
   int BN = 64;
   if (d->Cout % 256 == 0 && (int64_t)g.m_tiles * (d->Cout / 256) >= sm_count()) BN = 256;
@@ -437,8 +694,9 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
     SRGD_REQUIRE(d->Cout % 8 == 0 && (d->Cout / 8) % 8 == 0, "conv: GroupNorm partials need Cout %% 64 == 0");
     SRGD_REQUIRE(g.tn_log2 <= 2, "conv: GroupNorm partials need H*W >= 32 (got %dx%d)", d->Ho, d->Wo);
     while (BN < d->Cout / 8) BN *= 2;                    // a tile must hold whole groups
-    SRGD_REQUIRE(BN <= 256 && d->Cout % BN == 0, "conv: cannot tile Cout=%d for GroupNorm partials", d->Cout);
+      SRGD_REQUIRE(BN <= 256 && d->Cout % BN == 0, "conv: cannot tile Cout=%d for GroupNorm partials", d->Cout);
   }
+  if (swapped) BN = 128;
 
   ConvKernelParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -487,7 +745,7 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   kp.tiles_x = g.tiles_x; kp.tiles_y = g.tiles_y; kp.tiles_b = g.tiles_b;
   kp.m_tiles = g.m_tiles;
   kp.n_tiles = (d->Cout + BN - 1) / BN;
-  kp.total_tiles = kp.m_tiles * kp.n_tiles;
+  kp.total_tiles = (swapped ? (kp.m_tiles + 1) / 2 : kp.m_tiles) * kp.n_tiles;
   kp.group_size = d->Cout / 8;
   kp.act = d->act; kp.out_mode = d->out_mode;
   kp.bias = d->bias; kp.row_scale = d->row_scale;
@@ -499,6 +757,7 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   const double M = (double)d->B * d->Ho * d->Wo;
   ProfScope prof(SRGD_PK_CONV, 2.0 * M * d->Cout * total_kb * kBK,
                  2.0 * (M * total_kb * kBK + (double)d->Cout * d->Ktot + M * d->Cout), st);
+  if (swapped) return launch_igemm_t(kp, st);
   switch (BN) {
     case 64: return launch_igemm<64, 8>(kp, st);
     case 128: return launch_igemm<128, 6>(kp, st);

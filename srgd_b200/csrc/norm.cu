@@ -117,23 +117,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
   const bf16* xs = x + (int64_t)bs * HW * C;
   const bf16* rs = HAS_RES ? residual + (int64_t)b * HW * C : nullptr;
   bf16* ys = y + (int64_t)b * HW * C;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vec_per_pix) * 8;
-    float f[8];
-    unpack8(ld_stream(xs + i * 8), f);
-    const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
-    f[0] = silu_f(fmaf(f[0], a0.x, b0.x)); f[1] = silu_f(fmaf(f[1], a0.y, b0.y));
-    f[2] = silu_f(fmaf(f[2], a0.z, b0.z)); f[3] = silu_f(fmaf(f[3], a0.w, b0.w));
-    f[4] = silu_f(fmaf(f[4], a1.x, b1.x)); f[5] = silu_f(fmaf(f[5], a1.y, b1.y));
-    f[6] = silu_f(fmaf(f[6], a1.z, b1.z)); f[7] = silu_f(fmaf(f[7], a1.w, b1.w));
+  // two independent 16-byte vectors in flight per thread per iteration (memory-level parallelism)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool has1 = i1 < total;
+    uint4 xv[2], rv[2];
+    xv[0] = ld_stream(xs + i * 8);
+    if (has1) xv[1] = ld_stream(xs + i1 * 8);
     if (HAS_RES) {
-      float r[8];
-      unpack8(ld_stream(rs + i * 8), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+      rv[0] = ld_stream(rs + i * 8);
+      if (has1) rv[1] = ld_stream(rs + i1 * 8);
     }
-    st_stream(ys + i * 8, pack8(f));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const int64_t iu = u ? i1 : i;
+      const int c0 = (int)(iu % vec_per_pix) * 8;
+      float f[8];
+      unpack8(xv[u], f);
+      const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
+      f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y);
+      f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+      f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y);
+      f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+      silu2(f[0], f[1]); silu2(f[2], f[3]); silu2(f[4], f[5]); silu2(f[6], f[7]);
+      if (HAS_RES) {
+        float r[8];
+        unpack8(rv[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      st_stream(ys + iu * 8, pack8(f));
+    }
   }
 }
 

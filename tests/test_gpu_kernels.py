@@ -90,12 +90,26 @@ CONV_CASES = [
     (1, 40, 24, [128], 128, 3),           # partial tiles in x and y
     (2, 32, 32, [64], 64, 3),             # BN=64 instance
     (1, 32, 32, [1024, 512], 1024, 1),    # long-K 1x1 over a concat
+    (1, 24, 40, [128], 128, 3),           # odd number of pixel tiles (channels-as-M pairs them)
+    (5, 16, 16, [128], 384, 1),
 ]
+
+
+@pytest.fixture(params=["auto", "n"])
+def conv_variant(request):
+    """auto: channels-as-M kernel for 128-wide Cout slabs; n: force the pixels-as-M kernel."""
+    import os
+    if request.param == "n":
+        os.environ["SRGD_CONV_VARIANT"] = "n"
+    yield request.param
+    os.environ.pop("SRGD_CONV_VARIANT", None)
 
 
 @pytest.mark.parametrize("B,H,W,cins,Cout,ks", CONV_CASES)
 @pytest.mark.parametrize("direct", [False, True])
-def test_conv_matches_torch(lib, B, H, W, cins, Cout, ks, direct):
+def test_conv_matches_torch(lib, conv_variant, B, H, W, cins, Cout, ks, direct):
+    if direct and conv_variant == "n":
+        pytest.skip("direct path has no variants")
     g = torch.Generator().manual_seed(B * 1000 + H + Cout)
     xs = [G.bf16_round(torch.randn(B, c, H, W, generator=g)) for c in cins]
     cin = sum(cins)
@@ -194,7 +208,7 @@ def test_init_conv_pack_and_7tap(lib):
 # GroupNorm / RMSNorm
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64)])
-def test_groupnorm_fused_stats_and_apply(lib, B, H, W, C):
+def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     g = torch.Generator().manual_seed(C + H)
     Cin = 128
     x = G.bf16_round(torch.randn(B, Cin, H, W, generator=g))
