@@ -160,9 +160,28 @@ int srgd_rmsnorm_residual(const void* x, const float* g, const void* residual, v
 size_t srgd_linear_attention_workspace(int32_t B, int32_t N, int32_t heads);
 int srgd_linear_attention(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,
                           void* workspace, size_t workspace_bytes, srgd_stream_t stream);
+/* Whole LinearAttention block fused on tcgen05 (model.py:307-324 + the caller's "+ x", 703/718):
+ * out = RMSNorm_g(to_out(linear_attention(to_qkv(RMSNorm(x))))) + x, bf16 [B][N][C] in and out.
+ * qkv_w: bf16 [3*heads*32][C] with the pre-norm gain g*sqrt(C) folded into its columns; out_w: bf16
+ * [C][heads*32]; out_b, out_g: fp32 [C].  q/k/v/o never leave the SM (TMEM + shared memory).
+ * Supported shapes only (srgd_linear_attention_block_supported: heads=4, C in {128,256}, N % 128 == 0);
+ * other shapes use srgd_pixel_inv_norm + srgd_conv_igemm + srgd_linear_attention + srgd_rmsnorm_residual. */
+int srgd_linear_attention_block_supported(int32_t N, int32_t C, int32_t heads);
+size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, int32_t C, int32_t heads);
+int srgd_linear_attention_block(const void* x, const void* qkv_w, const void* out_w, const float* out_b,
+                                const float* out_g, void* out, int32_t B, int32_t N, int32_t C,
+                                int32_t heads, void* workspace, size_t workspace_bytes,
+                                srgd_stream_t stream);
 /* Full attention core (Attend, model.py:352): softmax(q k^T * 32^-1/2) v -> bf16 [B][N][heads*32]. */
 int srgd_attention(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,
                    srgd_stream_t stream);
+
+/* Same contract as srgd_attention on the tcgen05 tensor cores (flash-style: S = Q K^T and P V are
+ * tcgen05.mma with TMEM accumulators, online softmax in fp32).  Needs N % 128 == 0, heads <= 4
+ * (srgd_attention_tc_supported); the U-Net launcher falls back to srgd_attention otherwise. */
+int srgd_attention_tc_supported(int32_t N, int32_t heads);
+int srgd_attention_tc(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,
+                      srgd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * U-Net entry and exit (model.py:681-687, 722-725) and embeddings (model.py:223-238, 603-619, 264-267)

@@ -75,7 +75,12 @@ SIGNATURES = {
     "srgd_rmsnorm_residual": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "srgd_linear_attention_workspace": (_SZ, [_I32, _I32, _I32]),
     "srgd_linear_attention": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _SZ, _P]),
+    "srgd_linear_attention_block_supported": (C.c_int, [_I32, _I32, _I32]),
+    "srgd_linear_attention_block_workspace": (_SZ, [_I32, _I32, _I32, _I32]),
+    "srgd_linear_attention_block": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
     "srgd_attention": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "srgd_attention_tc_supported": (C.c_int, [_I32, _I32]),
+    "srgd_attention_tc": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
     "srgd_pack_input": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P]),
     "srgd_final_conv": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "srgd_dense_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tiles.h"
+#include "tmap.h"
 
 namespace srgd {
 
@@ -597,6 +598,51 @@ static EncodeTiledFn get_encode_tiled() {
       fn = reinterpret_cast<EncodeTiledFn>(ptr);
   }
   return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_rows, const char* what) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) {
+    set_error("%s: cuTensorMapEncodeTiled not available from the driver", what);
+    return SRGD_E_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)row_stride_bytes};
+  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled(inner=%llu rows=%llu pitch=%llu box=%ux%u) failed with %d", what,
+              (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner,
+              box_rows, (int)r);
+    return SRGD_E_CUDA;
+  }
+  return SRGD_OK;
+}
+
+// qkv tensor bf16 [rows][3*heads*32] viewed as [rows][3*heads segments][32 channels]; the box is 64 channels
+// wide, so channels 32..63 of every shared-memory row are out of range and read as zero (attention_tc.cu).
+int make_tmap_qk_heads(CUtensorMap* m, const void* qkv, int64_t rows, int heads) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) {
+    set_error("attention_tc: cuTensorMapEncodeTiled not available from the driver");
+    return SRGD_E_CUDA;
+  }
+  const cuuint64_t gdim[3] = {32, (cuuint64_t)(3 * heads), (cuuint64_t)rows};
+  const cuuint64_t gstr[2] = {64, (cuuint64_t)(3 * heads * 32 * 2)};
+  const cuuint32_t box[3] = {64, 1, 128};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention_tc: cuTensorMapEncodeTiled(rows=%lld heads=%d) failed with %d", (long long)rows, heads, (int)r);
+    return SRGD_E_CUDA;
+  }
+  return SRGD_OK;
 }
 
 static int validate_desc(const srgd_conv_desc* d) {

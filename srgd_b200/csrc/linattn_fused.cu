@@ -1,0 +1,679 @@
+// Fused LinearAttention block on tcgen05 tensor cores (reference: LinearAttention.forward,
+// model.py:307-324, plus the caller's residual `attn(x) + x`, model.py:703/718):
+//
+//     xn = RMSNorm(x)                               (model.py:310; gain folded into the qkv weight)
+//     q,k,v = to_qkv(xn)                            1x1 conv, no bias (model.py:311-313)
+//     q = softmax_d(q) * 32^-1/2 ; k = softmax_n(k) (model.py:315-318)
+//     ctx[d][e] = sum_n k[d][n] v[e][n]             (model.py:320)
+//     o[e][n]   = sum_d ctx[d][e] q[d][n]           (model.py:322)
+//     y = RMSNorm(to_out(o)) + x                    (model.py:303-304, 324, 703)
+//
+// The unfused path (conv_igemm.cu + attention.cu + norm.cu) moves ~3.8 KB per pixel through HBM at
+// C = 128 (qkv tensor written and re-read, o, y before the norm ...).  Here the block is two
+// persistent tcgen05 kernels that keep q/k/v/o entirely on chip:
+//
+//   la_ctx_kernel  : per 128-pixel tile  K^T,V^T[128 ch][128 px] = W_{k,v} x^T  (channels as the MMA M
+//                    dimension, so softmax over n is thread-local: TMEM lane = channel), P = exp(k - max)
+//                    and V^T go to shared memory as bf16 K-major operands, ctx_tile = P V via a second
+//                    MMA, merged into per-thread running (max, Z, ctx[32]) -- the online softmax.
+//                    Reads x once (2C B/pixel), writes 17 KB per CTA.
+//   la_merge_kernel: merges the per-CTA partials into bf16 block-diagonal matrices [B][128][128].
+//   la_out_kernel  : per 128-pixel tile  Q = x Wq^T (pixels as M: softmax over d is thread-local),
+//                    O = softmax(Q) * blockdiag(ctx), Y = O Wout^T, then bias + RMSNorm + residual in
+//                    the epilogue.  Reads x (2C B/pixel + an L2-hot re-read for the residual), writes y.
+//
+// Supported: heads*dim_head = 128, C in {128, 256}, N % 128 == 0; everything else takes the unfused path.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace srgd {
+
+constexpr int kLfHid = 128;             // heads * dim_head
+constexpr float kLfQScale = 0.17677669529663687f;   // 32^-1/2 (model.py:295, 318)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel A: context partials
+// ---------------------------------------------------------------------------------------------
+constexpr int kCtxStages = 3;
+struct alignas(64) LaCtxParams {
+  CUtensorMap x_map;                    // bf16 [B*N][C], box {64, 128}
+  CUtensorMap w_map;                    // bf16 [384][C] (q | k | v rows), box {64, 128}
+  const float* inv;                     // [B*N] 1/||x||
+  float* part;                          // [B][splits][128][34] = m, Z, ctx[32]
+  int32_t C, splits, tiles_per_sample;
+};
+struct LaCtxSmem {
+  static constexpr int kStageBytes = 3 * 16384;              // Wk | Wv | x, one 64-wide k-block each
+  static constexpr int kPOffset = kCtxStages * kStageBytes;
+  static constexpr int kVtOffset = kPOffset + 32768;
+  static constexpr int kInvOffset = kVtOffset + 32768;       // float [2][128]
+  static constexpr int kBarOffset = kInvOffset + 1024;
+  static constexpr int kTotal = kBarOffset + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ LaCtxParams p) {
+  using L = LaCtxSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kCtxStages;
+  uint64_t* kv_full = empty_bar + kCtxStages;
+  uint64_t* kv_empty = kv_full + 1;
+  uint64_t* pv_ready = kv_empty + 1;
+  uint64_t* ctx_full = pv_ready + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctx_full + 1);
+  float* inv_s = reinterpret_cast<float*>(smem + L::kInvOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int per = (p.tiles_per_sample + p.splits - 1) / p.splits;
+  const int t0 = min(sp * per, p.tiles_per_sample), t1 = min(t0 + per, p.tiles_per_sample);
+  const int ntiles = t1 - t0;
+  const int kblocks = p.C / 64;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kCtxStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(kv_full, 1);
+    ptx::mbar_init(kv_empty, 8);
+    ptx::mbar_init(pv_ready, 8);
+    ptx::mbar_init(ctx_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.x_map);
+      ptx::prefetch_tmap(&p.w_map);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr_smem, 512);                  // K^T [0,128) | V^T [128,256) | ctx tile [256,384)
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int row0 = (b * p.tiles_per_sample + t0 + it) * 128;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + stage * L::kStageBytes;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        ptx::tma_load_2d(dst, &p.w_map, &full_bar[stage], kb * 64, 128);           // W_k rows
+        ptx::tma_load_2d(dst + 16384, &p.w_map, &full_bar[stage], kb * 64, 256);   // W_v rows
+        ptx::tma_load_2d(dst + 32768, &p.x_map, &full_bar[stage], kb * 64, row0);
+        if (++stage == kCtxStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const uint32_t par = it & 1;
+      ptx::mbar_wait(kv_empty, par ^ 1);                  // epilogue has read the previous K^T / V^T
+      ptx::tc_fence_after();
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t base = ptx::smem_u32(smem + stage * L::kStageBytes);
+        const uint64_t wk = ptx::make_sw128_kmajor_desc(base);
+        const uint64_t wv = ptx::make_sw128_kmajor_desc(base + 16384);
+        const uint64_t xd = ptx::make_sw128_kmajor_desc(base + 32768);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+          ptx::umma_bf16_ss(tmem_base, wk + 2 * k, xd + 2 * k, idesc, accum);
+          ptx::umma_bf16_ss(tmem_base + 128, wv + 2 * k, xd + 2 * k, idesc, accum);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (kb == kblocks - 1) ptx::umma_commit(kv_full);
+        if (++stage == kCtxStages) { stage = 0; phase ^= 1; }
+      }
+      // ctx_tile[(h,d)][(h',e)] = sum_px P[(h,d)][px] * Vt[(h',e)][px]
+      ptx::mbar_wait(pv_ready, par);
+      ptx::tc_fence_after();
+      const uint32_t pb = ptx::smem_u32(smem + L::kPOffset), vb = ptx::smem_u32(smem + L::kVtOffset);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t pd = ptx::make_sw128_kmajor_desc(pb + (ks >> 2) * 16384) + 2 * (ks & 3);
+        const uint64_t vd = ptx::make_sw128_kmajor_desc(vb + (ks >> 2) * 16384) + 2 * (ks & 3);
+        ptx::umma_bf16_ss(tmem_base + 256, pd, vd, idesc, ks != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(ctx_full);
+    }
+  } else if (warp >= 2) {
+    // ================================== softmax / operand warps ==================================
+    const bool is_k = warp < 6;                            // warps 2-5: K^T rows, warps 6-9: V^T rows
+    const int q = warp & 3;                                // TMEM lane quarter (= head)
+    const int row = q * 32 + lane;                         // channel (h,d) resp. (h,e)
+    const int et = threadIdx.x - 64;                       // 0..255
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    uint8_t* tile_smem = smem + (is_k ? L::kPOffset : L::kVtOffset);
+    float m_run = -INFINITY, z_run = 0.f;
+    float ctx[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ctx[e] = 0.f;
+
+    for (int it = 0; it < ntiles; ++it) {
+      const uint32_t par = it & 1;
+      const int row0 = (b * p.tiles_per_sample + t0 + it) * 128;
+      float* invb = inv_s + par * 128;
+      if (et < 128) invb[et] = p.inv[row0 + et];
+      named_bar_sync(1, 256);
+      ptx::mbar_wait(kv_full, par);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_bits + (is_k ? 0u : 128u);
+      float m_t = -INFINITY, z_t = 0.f;
+      if (is_k) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m_t = fmaxf(m_t, __uint_as_float(v[j]) * invb[c * 32 + j]);
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        uint32_t w[16];
+        if (is_k) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = __expf(__uint_as_float(v[j]) * invb[c * 32 + j] - m_t);
+            const float p1 = __expf(__uint_as_float(v[j + 1]) * invb[c * 32 + j + 1] - m_t);
+            z_t += p0 + p1;
+            w[j >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            w[j >> 1] = pack_bf16(__uint_as_float(v[j]) * invb[c * 32 + j],
+                                  __uint_as_float(v[j + 1]) * invb[c * 32 + j + 1]);
+        }
+        uint8_t* kbase = tile_smem + (c >> 1) * 16384;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_shared_v4(kbase + ptx::sw128_offset(row, (c & 1) * 4 + jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2],
+                       w[4 * jj + 3]);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(kv_empty);
+        ptx::mbar_arrive(pv_ready);
+      }
+      if (is_k) {
+        ptx::mbar_wait(ctx_full, par);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_bits + 256 + q * 32, v);    // diagonal 32x32 block of head q
+        ptx::tmem_ld_wait();
+        const float m_new = fmaxf(m_run, m_t);
+        const float so = __expf(m_run - m_new), sn = __expf(m_t - m_new);
+        z_run = z_run * so + z_t * sn;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ctx[e] = ctx[e] * so + __uint_as_float(v[e]) * sn;
+        m_run = m_new;
+        ptx::tc_fence_before();
+      }
+    }
+    if (is_k) {
+      float* dst = p.part + (((int64_t)b * p.splits + sp) * kLfHid + row) * 34;
+      dst[0] = m_run;
+      dst[1] = z_run;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) dst[2 + e] = ctx[e];
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge: partials -> bd[b][(h,e)][(h,d)] = 32^-1/2 * ctx_h[d][e] / Z_h[d]  (bf16, block diagonal)
+// block = (b, h); thread = d
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) la_merge_bd_kernel(const float* __restrict__ part, bf16* __restrict__ bd,
+                                                         int splits) {
+  const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
+  const int d = threadIdx.x;
+  const float* base = part + (((int64_t)b * splits) * kLfHid + h * 32 + d) * 34;
+  const int64_t sstride = (int64_t)kLfHid * 34;
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, base[s * sstride]);
+  float z = 0.f, acc[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* src = base + s * sstride;
+    const float w = __expf(src[0] - m);
+    z += w * src[1];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, src[2 + e], acc[e]);
+  }
+  const float inv = kLfQScale / z;
+  bf16* out = bd + (int64_t)b * kLfHid * kLfHid;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    bf16* rowp = out + (h * 32 + e) * kLfHid;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) rowp[hh * 32 + d] = __float2bfloat16(hh == h ? acc[e] * inv : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel B: q softmax, context apply, to_out, RMSNorm, residual
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) LaOutParams {
+  CUtensorMap x_map;                    // bf16 [B*N][C], box {64, 128}
+  CUtensorMap w_map;                    // bf16 [384][C], box {64, 128} (rows 0..127 = W_q)
+  CUtensorMap bd_map;                   // bf16 [B*128][128], box {64, 128}
+  CUtensorMap wout_map;                 // bf16 [C][128], box {64, C}
+  const float* inv;
+  const float* bias;
+  const float* g;
+  const bf16* x;
+  bf16* out;
+  int32_t chunks, tiles_per_sample;
+};
+template <int C>
+struct LaOutSmem {
+  static constexpr int kStages = (C == 128) ? 3 : 2;
+  static constexpr int kStageBytes = 2 * 16384;              // x | Wq, one k-block each
+  static constexpr int kQsOffset = kStages * kStageBytes;    // softmax(q) / o as bf16 A operands (aliased)
+  static constexpr int kBdOffset = kQsOffset + 32768;
+  static constexpr int kWoutOffset = kBdOffset + 32768;      // 2 k-blocks of [C][64]
+  static constexpr int kSsqOffset = kWoutOffset + 2 * C * 128;   // float [2][2][128]
+  static constexpr int kBarOffset = kSsqOffset + 2048;
+  static constexpr int kTotal = kBarOffset + 128 + 1024;
+};
+
+template <int C>
+__global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ LaOutParams p) {
+  using L = LaOutSmem<C>;
+  constexpr int kStages = L::kStages;
+  constexpr int kblocks = C / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* const_full = empty_bar + kStages;
+  uint64_t* q_full = const_full + 1;
+  uint64_t* qs_ready = q_full + 1;
+  uint64_t* o_full = qs_ready + 1;
+  uint64_t* os_ready = o_full + 1;
+  uint64_t* y_full = os_ready + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(y_full + 1);
+  float* ssq_s = reinterpret_cast<float*>(smem + L::kSsqOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, ck = blockIdx.x;
+  const int per = (p.tiles_per_sample + p.chunks - 1) / p.chunks;
+  const int t0 = min(ck * per, p.tiles_per_sample), t1 = min(t0 + per, p.tiles_per_sample);
+  const int ntiles = t1 - t0;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(const_full, 1);
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(qs_ready, 8);
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(os_ready, 8);
+    ptx::mbar_init(y_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.x_map);
+      ptx::prefetch_tmap(&p.w_map);
+      ptx::prefetch_tmap(&p.bd_map);
+      ptx::prefetch_tmap(&p.wout_map);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr_smem, 512);                  // Q [0,128) | O [128,256) | Y [256,256+C)
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    if (ntiles > 0) {
+      ptx::mbar_arrive_expect_tx(const_full, 32768 + 2 * C * 128);
+      ptx::tma_load_2d(smem + L::kBdOffset, &p.bd_map, const_full, 0, b * 128);
+      ptx::tma_load_2d(smem + L::kBdOffset + 16384, &p.bd_map, const_full, 64, b * 128);
+      ptx::tma_load_2d(smem + L::kWoutOffset, &p.wout_map, const_full, 0, 0);
+      ptx::tma_load_2d(smem + L::kWoutOffset + C * 128, &p.wout_map, const_full, 64, 0);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int row0 = (b * p.tiles_per_sample + t0 + it) * 128;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + stage * L::kStageBytes;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        ptx::tma_load_2d(dst, &p.x_map, &full_bar[stage], kb * 64, row0);
+        ptx::tma_load_2d(dst + 16384, &p.w_map, &full_bar[stage], kb * 64, 0);     // W_q rows
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(128, 128);
+    constexpr uint32_t idescC = ptx::make_idesc_bf16_f32(128, C);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t qs = ptx::smem_u32(smem + L::kQsOffset), bdb = ptx::smem_u32(smem + L::kBdOffset);
+    const uint32_t wo = ptx::smem_u32(smem + L::kWoutOffset);
+    for (int it = 0; it < ntiles; ++it) {
+      const uint32_t par = it & 1;
+      // Q[px][(h,d)] = x Wq^T.  (The previous tile's Q/O/Y accumulators were drained before the epilogue
+      // signalled os_ready / finished, which this thread observed in program order.)
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t base = ptx::smem_u32(smem + stage * L::kStageBytes);
+        const uint64_t xd = ptx::make_sw128_kmajor_desc(base);
+        const uint64_t wq = ptx::make_sw128_kmajor_desc(base + 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_bf16_ss(tmem_base, xd + 2 * k, wq + 2 * k, idesc128, (kb | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&empty_bar[stage]);
+        if (kb == kblocks - 1) ptx::umma_commit(q_full);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (it == 0) ptx::mbar_wait(const_full, 0);
+      // O[px][(h,e)] = softmax(q)[px][(h,d)] * bd[(h,e)][(h,d)]^T
+      ptx::mbar_wait(qs_ready, par);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = ptx::make_sw128_kmajor_desc(qs + (ks >> 2) * 16384) + 2 * (ks & 3);
+        const uint64_t bd = ptx::make_sw128_kmajor_desc(bdb + (ks >> 2) * 16384) + 2 * (ks & 3);
+        ptx::umma_bf16_ss(tmem_base + 128, ad, bd, idesc128, ks != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(o_full);
+      // Y[px][c] = O[px][(h,e)] * Wout[c][(h,e)]^T
+      ptx::mbar_wait(os_ready, par);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = ptx::make_sw128_kmajor_desc(qs + (ks >> 2) * 16384) + 2 * (ks & 3);
+        const uint64_t bd = ptx::make_sw128_kmajor_desc(wo + (ks >> 2) * (C * 128)) + 2 * (ks & 3);
+        ptx::umma_bf16_ss(tmem_base + 256, ad, bd, idescC, ks != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(y_full);
+    }
+  } else if (warp >= 2) {
+    // ======================================= epilogue =======================================
+    // 8 warps: lane quarter q = warp & 3 selects the 32 pixels, `half` the column half this warp owns.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    uint8_t* qs_smem = smem + L::kQsOffset + half * 16384;   // k-block `half` of the A operand tile
+    const float sqrt_c = sqrtf((float)C);
+    constexpr int kYChunks = C / 64;                         // 32-column chunks per half
+
+    for (int it = 0; it < ntiles; ++it) {
+      const uint32_t par = it & 1;
+      const int64_t px = (int64_t)(b * p.tiles_per_sample + t0 + it) * 128 + row;
+      const float my_inv = p.inv[px];
+
+      // ---- q: softmax over the 32 channels of each head (model.py:315) ----
+      ptx::mbar_wait(q_full, par);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_bits + (half * 2 + i) * 32, v);
+        ptx::tmem_ld_wait();
+        float f[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]) * my_inv;
+          mx = fmaxf(mx, f[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __expf(f[j] - mx);
+          sum += f[j];
+        }
+        const float rs = 1.0f / sum;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_shared_v4(qs_smem + ptx::sw128_offset(row, i * 4 + jj), pack_bf16(f[8 * jj] * rs, f[8 * jj + 1] * rs),
+                       pack_bf16(f[8 * jj + 2] * rs, f[8 * jj + 3] * rs),
+                       pack_bf16(f[8 * jj + 4] * rs, f[8 * jj + 5] * rs),
+                       pack_bf16(f[8 * jj + 6] * rs, f[8 * jj + 7] * rs));
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(qs_ready);
+
+      // ---- o -> bf16 A operand (same shared-memory tile: the O MMA has consumed softmax(q)) ----
+      ptx::mbar_wait(o_full, par);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_bits + 128 + (half * 2 + i) * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_shared_v4(qs_smem + ptx::sw128_offset(row, i * 4 + jj),
+                       pack_bf16(__uint_as_float(v[8 * jj]), __uint_as_float(v[8 * jj + 1])),
+                       pack_bf16(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3])),
+                       pack_bf16(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5])),
+                       pack_bf16(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7])));
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(os_ready);
+
+      // ---- y: + bias, RMSNorm over all C channels of the pixel (model.py:207), * g, + x ----
+      ptx::mbar_wait(y_full, par);
+      ptx::tc_fence_after();
+      const uint32_t ycol0 = 256 + half * (C / 2);
+      const int c_first = half * (C / 2);
+      float ssq = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < kYChunks; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_bits + ycol0 + cc * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + j));
+          const float y0 = __uint_as_float(v[j]) + bv.x, y1 = __uint_as_float(v[j + 1]) + bv.y;
+          const float y2 = __uint_as_float(v[j + 2]) + bv.z, y3 = __uint_as_float(v[j + 3]) + bv.w;
+          ssq += y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
+        }
+      }
+      float* ssq_t = ssq_s + par * 256;
+      ssq_t[half * 128 + row] = ssq;
+      named_bar_sync(1, 256);
+      const float tot = ssq_t[row] + ssq_t[128 + row];
+      const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
+      const bf16* xrow = p.x + px * C + c_first;
+      bf16* orow = p.out + px * C + c_first;
+#pragma unroll 1
+      for (int cc = 0; cc < kYChunks; ++cc) {
+        uint4 xr[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) xr[jj] = *reinterpret_cast<const uint4*>(xrow + cc * 32 + jj * 8);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_bits + ycol0 + cc * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float r[8], o[8];
+          unpack8(xr[jj], r);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8 + 4));
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8 + 4));
+          o[0] = (__uint_as_float(v[jj * 8 + 0]) + b0.x) * scale * g0.x + r[0];
+          o[1] = (__uint_as_float(v[jj * 8 + 1]) + b0.y) * scale * g0.y + r[1];
+          o[2] = (__uint_as_float(v[jj * 8 + 2]) + b0.z) * scale * g0.z + r[2];
+          o[3] = (__uint_as_float(v[jj * 8 + 3]) + b0.w) * scale * g0.w + r[3];
+          o[4] = (__uint_as_float(v[jj * 8 + 4]) + b1.x) * scale * g1.x + r[4];
+          o[5] = (__uint_as_float(v[jj * 8 + 5]) + b1.y) * scale * g1.y + r[5];
+          o[6] = (__uint_as_float(v[jj * 8 + 6]) + b1.z) * scale * g1.z + r[6];
+          o[7] = (__uint_as_float(v[jj * 8 + 7]) + b1.w) * scale * g1.w + r[7];
+          st_stream(orow + cc * 32 + jj * 8, pack8(o));
+        }
+      }
+      ptx::tc_fence_before();
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int la_splits_for(int B, int tiles_per_sample) {
+  int s = sm_count() / B;
+  if (s < 1) s = 1;
+  if (s > tiles_per_sample) s = tiles_per_sample;
+  return s;
+}
+
+template <int C>
+static int launch_la_out(const LaOutParams& kp, int chunks, int B, cudaStream_t st) {
+  using L = LaOutSmem<C>;
+  static bool configured = false;
+  if (!configured) {
+    SRGD_CUDA_OK(cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  la_out_kernel<C><<<dim3(chunks, B), 320, L::kTotal, st>>>(kp);
+  SRGD_LAUNCH_OK("la_out_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+}  // namespace srgd
+
+using namespace srgd;
+
+extern "C" int srgd_linear_attention_block_supported(int32_t N, int32_t C, int32_t heads) {
+  return (heads == 4 && (C == 128 || C == 256) && N > 0 && N % 128 == 0) ? 1 : 0;
+}
+
+extern "C" size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, int32_t C, int32_t heads) {
+  if (!srgd_linear_attention_block_supported(N, C, heads) || B <= 0) return 0;
+  const int splits = la_splits_for(B, N / 128);
+  return (size_t)B * N * sizeof(float) + (size_t)B * splits * kLfHid * 34 * sizeof(float) +
+         (size_t)B * kLfHid * kLfHid * 2 + 1024;
+}
+
+extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, const void* out_w, const float* out_b,
+                                           const float* out_g, void* out, int32_t B, int32_t N, int32_t C,
+                                           int32_t heads, void* workspace, size_t workspace_bytes,
+                                           srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && qkv_w && out_w && out_b && out_g && out && workspace && B > 0, "linear_attention_block: null argument");
+  SRGD_REQUIRE(srgd_linear_attention_block_supported(N, C, heads),
+               "linear_attention_block: unsupported shape N=%d C=%d heads=%d (need heads=4, C in {128,256}, N %% 128 == 0)",
+               N, C, heads);
+  SRGD_REQUIRE(B <= 65535, "linear_attention_block: B too large");
+  SRGD_REQUIRE(((uintptr_t)x | (uintptr_t)qkv_w | (uintptr_t)out_w | (uintptr_t)out | (uintptr_t)workspace) % 16 == 0,
+               "linear_attention_block: pointers must be 16-byte aligned");
+  if (workspace_bytes < srgd_linear_attention_block_workspace(B, N, C, heads)) {
+    set_error("linear_attention_block: workspace too small");
+    return SRGD_E_WORKSPACE;
+  }
+  const int tiles = N / 128;
+  const int splits = la_splits_for(B, tiles);
+  const int64_t M = (int64_t)B * N;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* inv = reinterpret_cast<float*>(ws);
+  size_t off = ((size_t)M * sizeof(float) + 255) & ~(size_t)255;
+  float* part = reinterpret_cast<float*>(ws + off);
+  off += ((size_t)B * splits * kLfHid * 34 * sizeof(float) + 255) & ~(size_t)255;
+  bf16* bd = reinterpret_cast<bf16*>(ws + off);
+  cudaStream_t st = as_stream(stream);
+
+  rc = srgd_pixel_inv_norm(x, inv, M, C, stream);
+  if (rc) return rc;
+
+  ProfScope prof(SRGD_PK_LINEAR_ATTN, 2.0 * (double)M * ((double)C * 384 + 128.0 * 128 * 2 + 128.0 * C),
+                 (double)M * C * 2.0 * 2.0, st);
+  LaCtxParams ap;
+  memset(&ap, 0, sizeof(ap));
+  rc = make_tmap_2d_bf16(&ap.x_map, x, C, M, (uint64_t)C * 2, 64, 128, "linear_attention_block(x)");
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&ap.w_map, qkv_w, C, 384, (uint64_t)C * 2, 64, 128, "linear_attention_block(qkv_w)");
+  if (rc) return rc;
+  ap.inv = inv; ap.part = part; ap.C = C; ap.splits = splits; ap.tiles_per_sample = tiles;
+  static bool configured = false;
+  if (!configured) {
+    SRGD_CUDA_OK(cudaFuncSetAttribute(la_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaCtxSmem::kTotal));
+    configured = true;
+  }
+  la_ctx_kernel<<<dim3(splits, B), 320, LaCtxSmem::kTotal, st>>>(ap);
+  SRGD_LAUNCH_OK("la_ctx_kernel");
+  la_merge_bd_kernel<<<B * 4, 32, 0, st>>>(part, bd, splits);
+  SRGD_LAUNCH_OK("la_merge_bd_kernel");
+  count_launch(2);
+
+  LaOutParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.x_map = ap.x_map;
+  bp.w_map = ap.w_map;
+  rc = make_tmap_2d_bf16(&bp.bd_map, bd, 128, (uint64_t)B * 128, 256, 64, 128, "linear_attention_block(ctx)");
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&bp.wout_map, out_w, 128, C, 256, 64, C, "linear_attention_block(out_w)");
+  if (rc) return rc;
+  bp.inv = inv; bp.bias = out_b; bp.g = out_g;
+  bp.x = reinterpret_cast<const bf16*>(x);
+  bp.out = reinterpret_cast<bf16*>(out);
+  bp.chunks = splits; bp.tiles_per_sample = tiles;
+  if (C == 128) return launch_la_out<128>(bp, splits, B, st);
+  return launch_la_out<256>(bp, splits, B, st);
+}

@@ -335,6 +335,18 @@ struct Fwd {
   void* attention(const AttnP& a, const void* x, int H, int W) {
     const size_t M = (size_t)B * H * W;
     const int hid = u.hidden;
+    if (!a.full && !(conv_impl & 1) && srgd_linear_attention_block_supported(H * W, a.C, u.cfg.heads)) {
+      // fused tcgen05 block: q/k/v/o stay on chip (linattn_fused.cu)
+      const size_t wsb = srgd_linear_attention_block_workspace(B, H * W, a.C, u.cfg.heads);
+      void* lws = alloc(wsb);
+      void* out = alloc(M * a.C * 2);
+      if (!dry && ok())
+        run(srgd_linear_attention_block(x, a.qkv_w, a.out_w, a.out_b, a.out_g, out, B, H * W, a.C, u.cfg.heads, lws,
+                                        wsb, st));
+      ar.release(lws);
+      tap(a.name, out, M * a.C * 2);
+      return out;
+    }
     float* inv = reinterpret_cast<float*>(alloc(M * sizeof(float)));
     if (!dry && ok()) run(srgd_pixel_inv_norm(x, inv, (int64_t)M, a.C, st));
     void* qkv = alloc(M * 3 * hid * 2);
@@ -343,7 +355,12 @@ struct Fwd {
     void* ao = alloc(M * hid * 2);
     void* out = nullptr;
     if (a.full) {
-      if (!dry && ok()) run(srgd_attention(qkv, ao, B, H * W, u.cfg.heads, st));
+      if (!dry && ok()) {
+        if (!(conv_impl & 1) && srgd_attention_tc_supported(H * W, u.cfg.heads))
+          run(srgd_attention_tc(qkv, ao, B, H * W, u.cfg.heads, st));       // tcgen05 flash attention
+        else
+          run(srgd_attention(qkv, ao, B, H * W, u.cfg.heads, st));          // CUDA-core path (small N / debug)
+      }
       ar.release(qkv);
       ar.release(inv);
       out = alloc(M * a.C * 2);
@@ -566,10 +583,15 @@ extern "C" void srgd_unet_destroy(srgd_unet* u) { delete u; }
 
 extern "C" size_t srgd_unet_workspace_bytes(const srgd_unet* u, int32_t B, int32_t H, int32_t W) {
   if (check_shape(u, B, H, W) != SRGD_OK) return 0;
-  Arena ar(nullptr, (size_t)1 << 60);
-  forward_impl(*const_cast<srgd_unet*>(u), ar, true, nullptr, nullptr, nullptr, nullptr, 0, B, nullptr, B, H, W, 0,
-               nullptr);
-  return ar.high_water() + 256;
+  // the product plan and the debug plan (conv_impl bit 0: unfused attention) differ: size for both
+  size_t need = 0;
+  for (int impl = 0; impl < 2; ++impl) {
+    Arena ar(nullptr, (size_t)1 << 60);
+    forward_impl(*const_cast<srgd_unet*>(u), ar, true, nullptr, nullptr, nullptr, nullptr, 0, B, nullptr, B, H, W, impl,
+                 nullptr);
+    if (ar.high_water() > need) need = ar.high_water();
+  }
+  return need + 256;
 }
 
 extern "C" int srgd_unet_forward(srgd_unet* u, const float* x_dev, const float* cond_dev, const float* log_snr_dev,

@@ -287,6 +287,50 @@ def test_linear_attention_core(lib, B, N):
     assert rel_err(out.float().cpu(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (1, 64, 128, 128), (3, 16, 8, 256), (2, 64, 64, 256),
+                                     (20, 16, 16, 128)])
+def test_linear_attention_block_fused(lib, B, H, W, C):
+    """Whole LinearAttention block + residual on tcgen05 (linattn_fused.cu) vs the oracle's
+    _linear_attention (model.py:287-324) + x (model.py:703)."""
+    g = torch.Generator().manual_seed(B * 1000 + H + C)
+    N = H * W
+    assert lib.srgd_linear_attention_block_supported(N, C, 4) == 1
+    x = G.bf16_round(torch.randn(B, C, H, W, generator=g) * 1.3)
+    sd = {"a.norm.g": (1 + 0.1 * torch.randn(1, C, 1, 1, generator=g)),
+          "a.to_qkv.weight": torch.randn(384, C, 1, 1, generator=g) * (2.0 / math.sqrt(C)),
+          "a.to_out.0.weight": torch.randn(C, 128, 1, 1, generator=g) * (1.0 / math.sqrt(128)),
+          "a.to_out.0.bias": torch.randn(C, generator=g) * 0.1,
+          "a.to_out.1.g": (1 + 0.1 * torch.randn(1, C, 1, 1, generator=g))}
+    # the kernel sees bf16 weights with the pre-norm gain folded in (srgd_b200/weights.py)
+    wq = G.bf16_round(sd["a.to_qkv.weight"].reshape(384, C) * (sd["a.norm.g"].reshape(1, C) * math.sqrt(C)))
+    wo = G.bf16_round(sd["a.to_out.0.weight"].reshape(C, 128))
+    ref_sd = dict(sd)
+    ref_sd["a.norm.g"] = torch.ones(1, C, 1, 1) / math.sqrt(C) * 1.0          # gain already inside wq
+    ref_sd["a.to_qkv.weight"] = wq.reshape(384, C, 1, 1)
+    ref_sd["a.to_out.0.weight"] = wo.reshape(C, 128, 1, 1)
+    ref = O._linear_attention(ref_sd, "a", x, 4, 32) + x
+    xd = G.nhwc_bf16(x)
+    out = torch.empty_like(xd)
+    wsb = lib.srgd_linear_attention_block_workspace(B, N, C, 4)
+    ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.srgd_linear_attention_block(G.P(xd), G.P(wq.cuda().bfloat16()), G.P(wo.cuda().bfloat16()),
+                                               G.P(sd["a.to_out.0.bias"].cuda()),
+                                               G.P(sd["a.to_out.1.g"].reshape(-1).contiguous().cuda()), G.P(out), B, N, C, 4,
+                                               G.P(ws), wsb, G.stream()), "linear_attention_block")
+    torch.cuda.synchronize()
+    got = G.to_nchw_f32(out)
+    err = (got - ref).abs()
+    print(f"fused LA block B={B} {H}x{W} C={C}: max {float(err.max()):.4f} rms {float(err.pow(2).mean().sqrt()):.5f} "
+          f"ref rms {float(ref.pow(2).mean().sqrt()):.3f}")
+    assert rel_err(got, ref) < 1.5e-2
+
+
+def test_linear_attention_block_unsupported_shapes(lib):
+    assert lib.srgd_linear_attention_block_supported(64, 128, 4) == 0       # N % 128 != 0
+    assert lib.srgd_linear_attention_block_supported(1024, 512, 4) == 0     # C = 512 takes the unfused path
+    assert lib.srgd_linear_attention_block_workspace(2, 64, 128, 4) == 0
+
+
 @pytest.mark.parametrize("B,N", [(2, 1024), (1, 64), (2, 100)])
 def test_full_attention_core(lib, B, N):
     g = torch.Generator().manual_seed(N + 1)
@@ -296,6 +340,22 @@ def test_full_attention_core(lib, B, N):
     out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.srgd_attention(G.P(qkv.cuda().bfloat16()), G.P(out), B, N, 4, G.stream()))
     torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,N", [(2, 1024), (1, 128), (3, 256), (16, 1024)])
+def test_full_attention_tcgen05(lib, B, N):
+    """tcgen05 flash attention (attention_tc.cu) vs the oracle's Attend restatement."""
+    g = torch.Generator().manual_seed(N + B)
+    assert lib.srgd_attention_tc_supported(N, 4) == 1 and lib.srgd_attention_tc_supported(100, 4) == 0
+    qkv = G.bf16_round(torch.randn(B, N, 384, generator=g) * 1.5)
+    q, k, v = (t.reshape(B, N, 4, 32).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))   # b h n d
+    ref = O._attend(q, k, v).permute(0, 2, 1, 3).reshape(B, N, 128)
+    out = torch.empty(B, N, 128, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.srgd_attention_tc(G.P(qkv.cuda().bfloat16()), G.P(out), B, N, 4, G.stream()))
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs()
+    print(f"tcgen05 attention B={B} N={N}: max {float(err.max()):.4f} rms {float(err.pow(2).mean().sqrt()):.5f}")
     assert rel_err(out.float().cpu(), ref) < 1e-2
 
 
