@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--cpu_steps", type=int, default=2, help="timed CPU-baseline steps (B=1 tile each)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--dump_launches", type=str, default=None,
+                    help="write the per-launch CUDA-event table of one profiled step (kind, ms, TFLOP/s, GB/s) here")
     return ap.parse_args()
 
 
@@ -159,7 +161,7 @@ def main():
     import torch.distributed as dist
     from oracle import srgd_oracle as O           # only for the deterministic random-init weights + CPU arm
     import model as M
-    from srgd_b200 import _lib
+    from srgd_b200 import _lib, sharding
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -206,8 +208,7 @@ def main():
         img = run_steps(img, args.warmup, args.steps)
         out = diff._finalize(img)
         if world > 1:                              # the only collective: final gather of finished images
-            gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-            dist.gather(out, gathered, dst=0)
+            gathered = sharding.gather_rows(out, [B] * world, dst=0)
         e1.record()
         barrier()
         elapsed_ms = e0.elapsed_time(e1)
@@ -251,6 +252,15 @@ def main():
             prof = {k: dict(v, ms=v["ms"] / prof_steps, launches=v["launches"] // prof_steps,
                             flops=v["flops"] / prof_steps, bytes=v["bytes"] / prof_steps)
                     for k, v in _lib.profile_report().items()}
+            if args.dump_launches:
+                recs = _lib.profile_records()
+                per = len(recs) // prof_steps
+                with open(args.dump_launches, "w") as f:
+                    f.write("# one warm step of the bench workload, CUDA events around every library launch\n")
+                    f.write("idx kind ms tflops gbs\n")
+                    for i, (kind, ms, fl, by) in enumerate(recs[-per:]):
+                        f.write(f"{i} {kind} {ms:.4f} {fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f} "
+                                f"{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.0f}\n")
 
     if rank != 0:
         if world > 1:

@@ -268,6 +268,9 @@ int srgd_profile_end(void);
 /* Sums since srgd_profile_begin for one kind: device milliseconds, algorithmic FLOPs and bytes the
  * launches were credited with, number of API-level launches. */
 int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* launches);
+/* The individual records behind those sums, in launch order (valid after srgd_profile_end). */
+int srgd_profile_record_count(void);
+int srgd_profile_record(int index, int* kind, double* ms, double* flops, double* bytes);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,9 @@ SIGNATURES = {
     "srgd_profile_end": (C.c_int, []),
     "srgd_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int)]),
+    "srgd_profile_record_count": (C.c_int, []),
+    "srgd_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]),
 }
 
 PROFILE_KINDS = ["conv_igemm", "gn_apply", "sampler_step", "linear_attention", "full_attention", "norm_misc", "other"]
@@ -112,6 +115,17 @@ def profile_report():
         check(lib.srgd_profile_get(k, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)), "srgd_profile_get")
         out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
     return out
+
+def profile_records():
+    """[(kind name, ms, flops, bytes)] per API-level launch, in launch order (after srgd_profile_end)."""
+    lib = load()
+    out = []
+    for i in range(lib.srgd_profile_record_count()):
+        k, ms, fl, by = C.c_int(), C.c_double(), C.c_double(), C.c_double()
+        check(lib.srgd_profile_record(i, C.byref(k), C.byref(ms), C.byref(fl), C.byref(by)), "srgd_profile_record")
+        out.append((PROFILE_KINDS[k.value], ms.value, fl.value, by.value))
+    return out
+
 
 _lib = None
 

@@ -63,6 +63,11 @@ struct ProfRec {
   cudaEvent_t e0, e1;
 };
 static std::vector<ProfRec> g_prof_recs;
+struct ProfDone {
+  int kind;
+  double flops, bytes, ms;
+};
+static std::vector<ProfDone> g_prof_done;
 static double g_prof_ms[SRGD_PK_COUNT], g_prof_flops[SRGD_PK_COUNT], g_prof_bytes[SRGD_PK_COUNT];
 static int g_prof_n[SRGD_PK_COUNT];
 
@@ -104,6 +109,7 @@ int srgd_device_check(int device) {
 int srgd_profile_begin(void) {
   for (auto& r : srgd::g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   srgd::g_prof_recs.clear();
+  srgd::g_prof_done.clear();
   for (int k = 0; k < SRGD_PK_COUNT; ++k) {
     srgd::g_prof_ms[k] = srgd::g_prof_flops[k] = srgd::g_prof_bytes[k] = 0.0;
     srgd::g_prof_n[k] = 0;
@@ -123,6 +129,7 @@ int srgd_profile_end(void) {
       srgd::g_prof_flops[r.kind] += r.flops;
       srgd::g_prof_bytes[r.kind] += r.bytes;
       srgd::g_prof_n[r.kind] += 1;
+      srgd::g_prof_done.push_back({r.kind, r.flops, r.bytes, (double)ms});
     }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -140,6 +147,21 @@ int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* la
   if (flops) *flops = srgd::g_prof_flops[kind];
   if (bytes) *bytes = srgd::g_prof_bytes[kind];
   if (launches) *launches = srgd::g_prof_n[kind];
+  return SRGD_OK;
+}
+
+int srgd_profile_record_count(void) { return (int)srgd::g_prof_done.size(); }
+
+int srgd_profile_record(int index, int* kind, double* ms, double* flops, double* bytes) {
+  if (index < 0 || index >= (int)srgd::g_prof_done.size()) {
+    srgd::set_error("profile_record: index %d out of range", index);
+    return SRGD_E_ARG;
+  }
+  const srgd::ProfDone& d = srgd::g_prof_done[index];
+  if (kind) *kind = d.kind;
+  if (ms) *ms = d.ms;
+  if (flops) *flops = d.flops;
+  if (bytes) *bytes = d.bytes;
   return SRGD_OK;
 }
 
