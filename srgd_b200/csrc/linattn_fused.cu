@@ -24,6 +24,7 @@
 //
 // Supported: heads*dim_head = 128, C in {128, 256}, N % 128 == 0; everything else takes the unfused path.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -50,7 +51,7 @@ struct alignas(64) LaCtxParams {
   CUtensorMap x_map;                    // bf16 [B*N][C], box {64, 128}
   CUtensorMap w_map;                    // bf16 [384][C] (q | k | v rows), box {64, 128}
   const float* inv;                     // [B*N] 1/||x||
-  float* part;                          // [B][splits][128][34] = m, Z, ctx[32]
+  float* part;                          // [B][splits][34][128] = m, Z, ctx[32] per channel
   int32_t C, splits, tiles_per_sample;
 };
 struct LaCtxSmem {
@@ -243,11 +244,11 @@ __global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ 
       }
     }
     if (is_k) {
-      float* dst = p.part + (((int64_t)b * p.splits + sp) * kLfHid + row) * 34;
+      float* dst = p.part + ((int64_t)b * p.splits + sp) * (34 * kLfHid) + row;   // record layout [34][128]
       dst[0] = m_run;
-      dst[1] = z_run;
+      dst[kLfHid] = z_run;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) dst[2 + e] = ctx[e];
+      for (int e = 0; e < 32; ++e) dst[(2 + e) * kLfHid] = ctx[e];
     }
   }
 
@@ -260,15 +261,22 @@ __global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// merge: partials -> bd[b][(h,e)][(h,d)] = 32^-1/2 * ctx_h[d][e] / Z_h[d]  (bf16, block diagonal)
-// block = (b, h); thread = d
+// merge: partials -> per-sample output matrix
+//     Mb[b][c][(h,d)] = sum_e Wout[c][(h,e)] * 32^-1/2 * ctx_h[d][e] / Z_h[d]          (bf16 [B][C][128])
+// i.e. to_out applied to the normalised context once per sample, so that the output kernel needs a single
+// GEMM  y = softmax_d(q) Mb^T  instead of  o = softmax_d(q) ctx ; y = o Wout^T  (model.py:322-324).
+// block = (b, h), 128 threads: d = t & 31, quarter t >> 5 of the C output channels.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) la_merge_bd_kernel(const float* __restrict__ part, bf16* __restrict__ bd,
-                                                         int splits) {
+__global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restrict__ part, const bf16* __restrict__ wout,
+                                                          bf16* __restrict__ mb, int splits, int C) {
+  extern __shared__ uint8_t merge_smem[];                  // Wout[:, h*32:(h+1)*32] as bf16 [C][32]
   const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
-  const int d = threadIdx.x;
-  const float* base = part + (((int64_t)b * splits) * kLfHid + h * 32 + d) * 34;
-  const int64_t sstride = (int64_t)kLfHid * 34;
+  const int d = threadIdx.x & 31, cq = threadIdx.x >> 5;
+  uint4* wsm = reinterpret_cast<uint4*>(merge_smem);
+  for (int i = threadIdx.x; i < C * 4; i += 128)           // 4 x 16 B per output channel
+    wsm[i] = __ldg(reinterpret_cast<const uint4*>(wout + (int64_t)(i >> 2) * kLfHid + h * 32) + (i & 3));
+  const float* base = part + (int64_t)b * splits * (34 * kLfHid) + h * 32 + d;
+  const int64_t sstride = 34 * kLfHid;
   float m = -INFINITY;
   for (int s = 0; s < splits; ++s) m = fmaxf(m, base[s * sstride]);
   float z = 0.f, acc[32];
@@ -277,17 +285,26 @@ __global__ void __launch_bounds__(32) la_merge_bd_kernel(const float* __restrict
   for (int s = 0; s < splits; ++s) {
     const float* src = base + s * sstride;
     const float w = __expf(src[0] - m);
-    z += w * src[1];
+    z += w * src[kLfHid];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, src[2 + e], acc[e]);
+    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, src[(2 + e) * kLfHid], acc[e]);
   }
   const float inv = kLfQScale / z;
-  bf16* out = bd + (int64_t)b * kLfHid * kLfHid;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    bf16* rowp = out + (h * 32 + e) * kLfHid;
+  for (int e = 0; e < 32; ++e) acc[e] *= inv;
+  __syncthreads();
+  const int cper = C >> 2;
+#pragma unroll 2
+  for (int c = cq * cper; c < (cq + 1) * cper; ++c) {
+    float sum = 0.f;
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) rowp[hh * 32 + d] = __float2bfloat16(hh == h ? acc[e] * inv : 0.f);
+    for (int t = 0; t < 4; ++t) {
+      float f[8];
+      unpack8(wsm[c * 4 + t], f);                          // same address across the warp: broadcast
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum = fmaf(f[j], acc[t * 8 + j], sum);
+    }
+    mb[((int64_t)b * C + c) * kLfHid + h * 32 + d] = __float2bfloat16(sum);
   }
 }
 
@@ -297,8 +314,7 @@ __global__ void __launch_bounds__(32) la_merge_bd_kernel(const float* __restrict
 struct alignas(64) LaOutParams {
   CUtensorMap x_map;                    // bf16 [B*N][C], box {64, 128}
   CUtensorMap w_map;                    // bf16 [384][C], box {64, 128} (rows 0..127 = W_q)
-  CUtensorMap bd_map;                   // bf16 [B*128][128], box {64, 128}
-  CUtensorMap wout_map;                 // bf16 [C][128], box {64, C}
+  CUtensorMap mb_map;                   // bf16 [B*C][128] (la_merge_mb_kernel), box {64, C}
   const float* inv;
   const float* bias;
   const float* g;
@@ -310,10 +326,9 @@ template <int C>
 struct LaOutSmem {
   static constexpr int kStages = (C == 128) ? 3 : 2;
   static constexpr int kStageBytes = 2 * 16384;              // x | Wq, one k-block each
-  static constexpr int kQsOffset = kStages * kStageBytes;    // softmax(q) / o as bf16 A operands (aliased)
-  static constexpr int kBdOffset = kQsOffset + 32768;
-  static constexpr int kWoutOffset = kBdOffset + 32768;      // 2 k-blocks of [C][64]
-  static constexpr int kSsqOffset = kWoutOffset + 2 * C * 128;   // float [2][2][128]
+  static constexpr int kQsOffset = kStages * kStageBytes;    // softmax(q) as bf16 A operand
+  static constexpr int kMbOffset = kQsOffset + 32768;        // 2 k-blocks of [C][64]
+  static constexpr int kSsqOffset = kMbOffset + 2 * C * 128;     // float [2][2][128]
   static constexpr int kBarOffset = kSsqOffset + 2048;
   static constexpr int kTotal = kBarOffset + 128 + 1024;
 };
@@ -330,9 +345,7 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
   uint64_t* const_full = empty_bar + kStages;
   uint64_t* q_full = const_full + 1;
   uint64_t* qs_ready = q_full + 1;
-  uint64_t* o_full = qs_ready + 1;
-  uint64_t* os_ready = o_full + 1;
-  uint64_t* y_full = os_ready + 1;
+  uint64_t* y_full = qs_ready + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(y_full + 1);
   float* ssq_s = reinterpret_cast<float*>(smem + L::kSsqOffset);
 
@@ -350,8 +363,6 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
     ptx::mbar_init(const_full, 1);
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(qs_ready, 8);
-    ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(os_ready, 8);
     ptx::mbar_init(y_full, 1);
     ptx::fence_barrier_init();
   }
@@ -359,11 +370,10 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
     if (lane == 0) {
       ptx::prefetch_tmap(&p.x_map);
       ptx::prefetch_tmap(&p.w_map);
-      ptx::prefetch_tmap(&p.bd_map);
-      ptx::prefetch_tmap(&p.wout_map);
+      ptx::prefetch_tmap(&p.mb_map);
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_ptr_smem, 512);                  // Q [0,128) | O [128,256) | Y [256,256+C)
+    ptx::tmem_alloc(tmem_ptr_smem, 512);                  // Q [0,128) | Y [256,256+C)
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -374,11 +384,9 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
     if (ntiles > 0) {
-      ptx::mbar_arrive_expect_tx(const_full, 32768 + 2 * C * 128);
-      ptx::tma_load_2d(smem + L::kBdOffset, &p.bd_map, const_full, 0, b * 128);
-      ptx::tma_load_2d(smem + L::kBdOffset + 16384, &p.bd_map, const_full, 64, b * 128);
-      ptx::tma_load_2d(smem + L::kWoutOffset, &p.wout_map, const_full, 0, 0);
-      ptx::tma_load_2d(smem + L::kWoutOffset + C * 128, &p.wout_map, const_full, 64, 0);
+      ptx::mbar_arrive_expect_tx(const_full, 2 * C * 128);
+      ptx::tma_load_2d(smem + L::kMbOffset, &p.mb_map, const_full, 0, b * C);
+      ptx::tma_load_2d(smem + L::kMbOffset + C * 128, &p.mb_map, const_full, 64, b * C);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -399,12 +407,11 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
     constexpr uint32_t idescC = ptx::make_idesc_bf16_f32(128, C);
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t qs = ptx::smem_u32(smem + L::kQsOffset), bdb = ptx::smem_u32(smem + L::kBdOffset);
-    const uint32_t wo = ptx::smem_u32(smem + L::kWoutOffset);
+    const uint32_t qs = ptx::smem_u32(smem + L::kQsOffset), wo = ptx::smem_u32(smem + L::kMbOffset);
     for (int it = 0; it < ntiles; ++it) {
       const uint32_t par = it & 1;
       // Q[px][(h,d)] = x Wq^T.  (The previous tile's Q/O/Y accumulators were drained before the epilogue
-      // signalled os_ready / finished, which this thread observed in program order.)
+      // signalled qs_ready for this tile, which this thread observes below in program order.)
       for (int kb = 0; kb < kblocks; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
@@ -418,18 +425,8 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (it == 0) ptx::mbar_wait(const_full, 0);
-      // O[px][(h,e)] = softmax(q)[px][(h,d)] * bd[(h,e)][(h,d)]^T
+      // Y[px][c] = softmax(q)[px][(h,d)] * Mb[c][(h,d)]^T
       ptx::mbar_wait(qs_ready, par);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t ad = ptx::make_sw128_kmajor_desc(qs + (ks >> 2) * 16384) + 2 * (ks & 3);
-        const uint64_t bd = ptx::make_sw128_kmajor_desc(bdb + (ks >> 2) * 16384) + 2 * (ks & 3);
-        ptx::umma_bf16_ss(tmem_base + 128, ad, bd, idesc128, ks != 0 ? 1u : 0u);
-      }
-      ptx::umma_commit(o_full);
-      // Y[px][c] = O[px][(h,e)] * Wout[c][(h,e)]^T
-      ptx::mbar_wait(os_ready, par);
       ptx::tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
@@ -488,27 +485,6 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(qs_ready);
-
-      // ---- o -> bf16 A operand (same shared-memory tile: the O MMA has consumed softmax(q)) ----
-      ptx::mbar_wait(o_full, par);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + lane_bits + 128 + (half * 2 + i) * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          st_shared_v4(qs_smem + ptx::sw128_offset(row, i * 4 + jj),
-                       pack_bf16(__uint_as_float(v[8 * jj]), __uint_as_float(v[8 * jj + 1])),
-                       pack_bf16(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3])),
-                       pack_bf16(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5])),
-                       pack_bf16(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7])));
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(os_ready);
 
       // ---- y: + bias, RMSNorm over all C channels of the pixel (model.py:207), * g, + x ----
       ptx::mbar_wait(y_full, par);
@@ -575,6 +551,9 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
   }
 }
 
+int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, const float* out_b, const float* out_g,
+                       void* out, int B, int N, const float* inv, float* part, bf16* bd, int splits, cudaStream_t st);
+
 static int la_splits_for(int B, int tiles_per_sample) {
   int s = sm_count() / B;
   if (s < 1) s = 1;
@@ -607,8 +586,9 @@ extern "C" int srgd_linear_attention_block_supported(int32_t N, int32_t C, int32
 extern "C" size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, int32_t C, int32_t heads) {
   if (!srgd_linear_attention_block_supported(N, C, heads) || B <= 0) return 0;
   const int splits = la_splits_for(B, N / 128);
-  return (size_t)B * N * sizeof(float) + (size_t)B * splits * kLfHid * 34 * sizeof(float) +
-         (size_t)B * kLfHid * kLfHid * 2 + 1024;
+  // C = 128 runs two pipelines per CTA (linattn_pp.cu): two partial records per split
+  return (size_t)B * N * sizeof(float) + (size_t)B * 2 * splits * kLfHid * 34 * sizeof(float) +
+         (size_t)B * C * kLfHid * 2 + 1024;
 }
 
 extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, const void* out_w, const float* out_b,
@@ -635,7 +615,7 @@ extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, con
   float* inv = reinterpret_cast<float*>(ws);
   size_t off = ((size_t)M * sizeof(float) + 255) & ~(size_t)255;
   float* part = reinterpret_cast<float*>(ws + off);
-  off += ((size_t)B * splits * kLfHid * 34 * sizeof(float) + 255) & ~(size_t)255;
+  off += ((size_t)B * 2 * splits * kLfHid * 34 * sizeof(float) + 255) & ~(size_t)255;
   bf16* bd = reinterpret_cast<bf16*>(ws + off);
   cudaStream_t st = as_stream(stream);
 
@@ -644,6 +624,8 @@ extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, con
 
   ProfScope prof(SRGD_PK_LINEAR_ATTN, 2.0 * (double)M * ((double)C * 384 + 128.0 * 128 * 2 + 128.0 * C),
                  (double)M * C * 2.0 * 2.0, st);
+  if (C == 128 && getenv("SRGD_LA_SERIAL") == nullptr)     // test knob: force the single-pipeline kernels
+    return launch_la_block_pp(x, qkv_w, out_w, out_b, out_g, out, B, N, inv, part, bd, splits, st);
   LaCtxParams ap;
   memset(&ap, 0, sizeof(ap));
   rc = make_tmap_2d_bf16(&ap.x_map, x, C, M, (uint64_t)C * 2, 64, 128, "linear_attention_block(x)");
@@ -658,17 +640,15 @@ extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, con
   }
   la_ctx_kernel<<<dim3(splits, B), 320, LaCtxSmem::kTotal, st>>>(ap);
   SRGD_LAUNCH_OK("la_ctx_kernel");
-  la_merge_bd_kernel<<<B * 4, 32, 0, st>>>(part, bd, splits);
-  SRGD_LAUNCH_OK("la_merge_bd_kernel");
+  la_merge_mb_kernel<<<B * 4, 128, (size_t)C * 64, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, splits, C);
+  SRGD_LAUNCH_OK("la_merge_mb_kernel");
   count_launch(2);
 
   LaOutParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.x_map = ap.x_map;
   bp.w_map = ap.w_map;
-  rc = make_tmap_2d_bf16(&bp.bd_map, bd, 128, (uint64_t)B * 128, 256, 64, 128, "linear_attention_block(ctx)");
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&bp.wout_map, out_w, 128, C, 256, 64, C, "linear_attention_block(out_w)");
+  rc = make_tmap_2d_bf16(&bp.mb_map, bd, 128, (uint64_t)B * C, 256, 64, C, "linear_attention_block(Mb)");
   if (rc) return rc;
   bp.inv = inv; bp.bias = out_b; bp.g = out_g;
   bp.x = reinterpret_cast<const bf16*>(x);

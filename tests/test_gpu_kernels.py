@@ -325,6 +325,41 @@ def test_linear_attention_block_fused(lib, B, H, W, C):
     assert rel_err(got, ref) < 1.5e-2
 
 
+def test_linear_attention_block_reference_jumps(lib):
+    """Online softmax over n with a moving exponent reference: k logits that grow by hundreds of nats from tile to
+    tile force the 'redo with the exact max' and 'rescale the TMEM context' paths of la_ctx_pp_kernel."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C = 1, 32, 32, 128
+    N = H * W
+    x = torch.randn(B, C, H, W, generator=g)
+    ramp = torch.linspace(0.0005, 12.0, N).reshape(1, 1, H, W)                # later pixels point harder along e0
+    x[:, 0:1] = x[:, 0:1] * 0.1 + ramp * 8
+    x = G.bf16_round(x)
+    wqkv = torch.randn(384, C, generator=g) * (2.0 / math.sqrt(C))
+    wqkv[128:256, 0] += torch.linspace(-3, 3, 128) * 36                       # k rows with huge gain on channel 0
+    sd = {"a.norm.g": torch.ones(1, C, 1, 1) / math.sqrt(C), "a.to_qkv.weight": G.bf16_round(wqkv).reshape(384, C, 1, 1),
+          "a.to_out.0.weight": G.bf16_round(torch.randn(C, 128, generator=g) / math.sqrt(128)).reshape(C, 128, 1, 1),
+          "a.to_out.0.bias": torch.randn(C, generator=g) * 0.1,
+          "a.to_out.1.g": (1 + 0.1 * torch.randn(1, C, 1, 1, generator=g))}
+    ref = O._linear_attention(sd, "a", x, 4, 32) + x
+    k = torch.nn.functional.conv2d(torch.nn.functional.normalize(x, dim=1), sd["a.to_qkv.weight"])[:, 128:256]
+    assert float(k.reshape(128, -1).max(dim=1).values.max() - k.reshape(128, -1)[:, :64].max(dim=1).values.min()) > 60
+    xd = G.nhwc_bf16(x)
+    out = torch.empty_like(xd)
+    wsb = lib.srgd_linear_attention_block_workspace(B, N, C, 4)
+    ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.srgd_linear_attention_block(G.P(xd), G.P(sd["a.to_qkv.weight"].reshape(384, C).cuda().bfloat16()),
+                                               G.P(sd["a.to_out.0.weight"].reshape(C, 128).cuda().bfloat16()),
+                                               G.P(sd["a.to_out.0.bias"].cuda()),
+                                               G.P(sd["a.to_out.1.g"].reshape(-1).contiguous().cuda()), G.P(out), B, N, C, 4,
+                                               G.P(ws), wsb, G.stream()), "linear_attention_block")
+    torch.cuda.synchronize()
+    got = G.to_nchw_f32(out)
+    assert torch.isfinite(got).all()
+    print(f"reference-jump LA block: max err {float((got - ref).abs().max()):.4f}, ref rms {float(ref.pow(2).mean().sqrt()):.3f}")
+    assert rel_err(got, ref) < 2e-2
+
+
 def test_linear_attention_block_unsupported_shapes(lib):
     assert lib.srgd_linear_attention_block_supported(64, 128, 4) == 0       # N % 128 != 0
     assert lib.srgd_linear_attention_block_supported(1024, 512, 4) == 0     # C = 512 takes the unfused path
