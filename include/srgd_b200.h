@@ -114,8 +114,8 @@ typedef struct srgd_conv_desc {
   int32_t act;             /* 0 none, 1 SiLU (applied after bias, before residual)             */
   int32_t out_mode;
   void* out;               /* bf16                                                             */
-  float* gn_partials;      /* NULL, or fp32 [m_tiles*4][8][2]: per (M-tile, epilogue warp) sum and
-                              sum of squares per GroupNorm group of the fp32 result (model.py:247) */
+  float* gn_partials;      /* NULL, or fp32 [m_tiles*8][8][2]: per (M-tile, pixel quarter, column half) sum
+                              and sum of squares per GroupNorm group of the fp32 result (model.py:247) */
 } srgd_conv_desc;
 
 /* Number of 128-pixel M tiles the kernel will use for (B,Ho,Wo) -- sizes gn_partials. */
@@ -137,11 +137,13 @@ int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int32_t H, int3
 /* y = SiLU( (GN(x)*gamma+beta) * (scale+1) + shift ) [+ residual].  scale_shift: fp32, row b at
  * scale_shift + b*ss_stride holds [scale(C) | shift(C)] (model.py:279), or NULL.  Row b of the
  * output reads sample (b % Bx) of x and stats (CFG halves sharing one conv result).  y may alias
- * x when Bx == B. */
+ * x when Bx == B.  inv_out (optional, residual variant with C in {128,256} only): fp32 [B*H*W],
+ * receives 1 / max(||y[pixel,:]||_2, 1e-12) of the stored bf16 row -- the RMSNorm statistic of the
+ * attention block that consumes y (model.py:207), saving srgd_pixel_inv_norm's extra pass. */
 int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
                          const float* beta, const float* scale_shift, int64_t ss_stride,
-                         const void* residual, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
-                         srgd_stream_t stream);
+                         const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
+                         int32_t C, srgd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * RMSNorm pieces (model.py:201-207)
@@ -162,15 +164,17 @@ int srgd_linear_attention(const void* qkv, void* out, int32_t B, int32_t N, int3
                           void* workspace, size_t workspace_bytes, srgd_stream_t stream);
 /* Whole LinearAttention block fused on tcgen05 (model.py:307-324 + the caller's "+ x", 703/718):
  * out = RMSNorm_g(to_out(linear_attention(to_qkv(RMSNorm(x))))) + x, bf16 [B][N][C] in and out.
+ * inv_norm: fp32 [B*N] = 1/max(||x[pixel,:]||,1e-12) if the producer already has it (srgd_groupnorm_apply
+ * inv_out), or NULL to compute it here.
  * qkv_w: bf16 [3*heads*32][C] with the pre-norm gain g*sqrt(C) folded into its columns; out_w: bf16
  * [C][heads*32]; out_b, out_g: fp32 [C].  q/k/v/o never leave the SM (TMEM + shared memory).
  * Supported shapes only (srgd_linear_attention_block_supported: heads=4, C in {128,256}, N % 128 == 0);
  * other shapes use srgd_pixel_inv_norm + srgd_conv_igemm + srgd_linear_attention + srgd_rmsnorm_residual. */
 int srgd_linear_attention_block_supported(int32_t N, int32_t C, int32_t heads);
 size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, int32_t C, int32_t heads);
-int srgd_linear_attention_block(const void* x, const void* qkv_w, const void* out_w, const float* out_b,
-                                const float* out_g, void* out, int32_t B, int32_t N, int32_t C,
-                                int32_t heads, void* workspace, size_t workspace_bytes,
+int srgd_linear_attention_block(const void* x, const float* inv_norm, const void* qkv_w, const void* out_w,
+                                const float* out_b, const float* out_g, void* out, int32_t B, int32_t N,
+                                int32_t C, int32_t heads, void* workspace, size_t workspace_bytes,
                                 srgd_stream_t stream);
 /* Full attention core (Attend, model.py:352): softmax(q k^T * 32^-1/2) v -> bf16 [B][N][heads*32]. */
 int srgd_attention(const void* qkv, void* out, int32_t B, int32_t N, int32_t heads,

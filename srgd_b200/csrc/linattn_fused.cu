@@ -591,9 +591,9 @@ extern "C" size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, in
          (size_t)B * C * kLfHid * 2 + 1024;
 }
 
-extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, const void* out_w, const float* out_b,
-                                           const float* out_g, void* out, int32_t B, int32_t N, int32_t C,
-                                           int32_t heads, void* workspace, size_t workspace_bytes,
+extern "C" int srgd_linear_attention_block(const void* x, const float* inv_norm, const void* qkv_w, const void* out_w,
+                                           const float* out_b, const float* out_g, void* out, int32_t B, int32_t N,
+                                           int32_t C, int32_t heads, void* workspace, size_t workspace_bytes,
                                            srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
@@ -619,8 +619,12 @@ extern "C" int srgd_linear_attention_block(const void* x, const void* qkv_w, con
   bf16* bd = reinterpret_cast<bf16*>(ws + off);
   cudaStream_t st = as_stream(stream);
 
-  rc = srgd_pixel_inv_norm(x, inv, M, C, stream);
-  if (rc) return rc;
+  if (inv_norm != nullptr) {
+    inv = const_cast<float*>(inv_norm);
+  } else {
+    rc = srgd_pixel_inv_norm(x, inv, M, C, stream);
+    if (rc) return rc;
+  }
 
   ProfScope prof(SRGD_PK_LINEAR_ATTN, 2.0 * (double)M * ((double)C * 384 + 128.0 * 128 * 2 + 128.0 * C),
                  (double)M * C * 2.0 * 2.0, st);

@@ -15,33 +15,51 @@ constexpr float kGnEps = 1e-5f;        // nn.GroupNorm default (model.py:247)
 constexpr int kGroups = 8;
 
 // ---- statistics ------------------------------------------------------------------------------
-// One block per (sample, group): fold the conv-epilogue partial sums (conv_igemm.cu) in fp64.
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partials,
+// One block per sample: fold the conv-epilogue partial sums (conv_igemm.cu) in fp64.  An entry is the 64-byte
+// record [8 groups][sum, sumsq] of one (tile, pixel quarter, column half); thread t reads float4 number (t & 3)
+// of every 256th entry, so a warp touches 8 whole records per load instruction; 1024 threads x 8 loads keep the
+// whole 256 KB of a 256x256 sample in flight at once (the kernel is pure memory latency).
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials,
                                                           float* __restrict__ stats, int H, int W, int C,
                                                           TileGeom g) {
-  const int n = blockIdx.x / kGroups, grp = blockIdx.x % kGroups;
+  const int n = blockIdx.x;
   const int tb = n >> g.tn_log2, n_i = n & ((1 << g.tn_log2) - 1);
   const int tiles_per_b = g.tiles_x * g.tiles_y;
   const int warps_per_sample = 4 >> g.tn_log2;           // tn_log2 <= 2 (checked by the conv launcher)
-  const int first_warp = n_i * warps_per_sample;
-  const int entries = tiles_per_b * warps_per_sample;
-  double s = 0.0, q = 0.0;
-  for (int e = threadIdx.x; e < entries; e += blockDim.x) {
-    const int t = e / warps_per_sample, w = e % warps_per_sample;
-    const float* p = partials + ((int64_t)((tb * tiles_per_b + t) * 4 + first_warp + w) * kGroups + grp) * 2;
-    s += (double)p[0];
-    q += (double)p[1];
+  const int per_tile = warps_per_sample * 2;             // two half-entries per (tile, pixel quarter)
+  const int entries = tiles_per_b * per_tile;
+  const int part = threadIdx.x & 3;                      // groups 2*part, 2*part+1
+  const float4* base = reinterpret_cast<const float4*>(partials) +
+                       ((int64_t)(tb * tiles_per_b) * 4 + n_i * warps_per_sample) * 2 * 4 + part;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  constexpr int kU = 8;                                  // independent 16-byte loads in flight per thread
+  for (int e0 = threadIdx.x >> 2; e0 < entries; e0 += 256 * kU) {
+    float4 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int e = e0 + u * 256;
+      // entry e -> tile e / per_tile, slot e % per_tile; records of one tile are 8 entries (4 quarters x 2) apart
+      v[u] = e < entries ? __ldg(base + ((int64_t)(e / per_tile) * 8 + (e % per_tile)) * 4) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) { a0 += v[u].x; a1 += v[u].y; a2 += v[u].z; a3 += v[u].w; }
   }
-  __shared__ double sh[2][4];
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+  // reduce over the threads with the same `part`: lanes xor 4, 8, 16, then the 8 warps through shared memory
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
   }
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __shared__ double sh[32][4][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) { sh[warp][lane][0] = a0; sh[warp][lane][1] = a1; sh[warp][lane][2] = a2; sh[warp][lane][3] = a3; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
-    q = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+  if (threadIdx.x < kGroups) {
+    const int grp = threadIdx.x, pt = grp >> 1, o = (grp & 1) * 2;
+    double s = 0.0, q = 0.0;
+    for (int w = 0; w < 32; ++w) { s += sh[w][pt][o]; q += sh[w][pt][o + 1]; }
     const double cnt = (double)H * W * (C / kGroups);
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;                  // biased variance, as nn.GroupNorm
@@ -85,12 +103,16 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 }
 
 // ---- apply -----------------------------------------------------------------------------------
-template <bool HAS_RES>
+// INV_LANES > 0: additionally emit inv_out[pixel] = 1 / max(||y[pixel,:]||_2, 1e-12) of the bf16-rounded output row
+// (the RMSNorm of the attention block that consumes y, model.py:207); the C/8 = INV_LANES threads of a pixel are
+// consecutive lanes of one warp.
+template <bool HAS_RES, int INV_LANES>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
-                                                       const bf16* residual, bf16* y, int HW, int C) {
+                                                       const bf16* residual, bf16* y, float* __restrict__ inv_out,
+                                                       int HW, int C) {
   extern __shared__ float sm[];                          // A[C] | B[C]
   float* sA = sm;
   float* sB = sm + C;
@@ -149,7 +171,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += r[j];
       }
-      st_stream(ys + iu * 8, pack8(f));
+      const uint4 packed = pack8(f);
+      st_stream(ys + iu * 8, packed);
+      if (INV_LANES > 0) {
+        float fr[8];
+        unpack8(packed, fr);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(fr[j], fr[j], ss);
+#pragma unroll
+        for (int o = INV_LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((threadIdx.x & (INV_LANES - 1)) == 0)
+          inv_out[(int64_t)b * HW + iu / vec_per_pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      }
     }
   }
 }
@@ -244,8 +278,8 @@ extern "C" int srgd_groupnorm_finalize(const float* gn_partials, float* stats, i
                "groupnorm_finalize: bad arguments");
   const TileGeom g = tile_geom(B, H, W);
   SRGD_REQUIRE(g.tn_log2 <= 2, "groupnorm_finalize: needs H*W >= 32");
-  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)g.m_tiles * 4 * 8 * 2 * 4, as_stream(stream));
-  gn_finalize_kernel<<<B * kGroups, 128, 0, as_stream(stream)>>>(gn_partials, stats, H, W, C, g);
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)g.m_tiles * 8 * 8 * 2 * 4, as_stream(stream));
+  gn_finalize_kernel<<<B, 1024, 0, as_stream(stream)>>>(gn_partials, stats, H, W, C, g);
   SRGD_LAUNCH_OK("gn_finalize_kernel");
   count_launch();
   return SRGD_OK;
@@ -265,8 +299,8 @@ extern "C" int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int3
 
 extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
                                     const float* beta, const float* scale_shift, int64_t ss_stride,
-                                    const void* residual, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
-                                    srgd_stream_t stream) {
+                                    const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
+                                    int32_t C, srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
   SRGD_REQUIRE(x && stats && gamma && beta && y, "groupnorm_apply: null argument");
@@ -282,12 +316,21 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   const bf16* rr = reinterpret_cast<const bf16*>(residual);
   bf16* yr = reinterpret_cast<bf16*>(y);
   ProfScope prof(SRGD_PK_GN_APPLY, 0.0, (double)B * H * W * C * (residual ? 6.0 : 4.0), as_stream(stream));
-  if (residual)
-    gn_apply_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride,
-                                                                  rr, yr, H * W, C);
+  SRGD_REQUIRE(inv_out == nullptr || (residual != nullptr && (C == 128 || C == 256) && (H * W) % 4 == 0),
+               "groupnorm_apply: inv_out needs the residual variant, C in {128, 256} and H*W %% 4 == 0");
+  cudaStream_t cst = as_stream(stream);
+  if (inv_out != nullptr && C == 128)
+    gn_apply_kernel<true, 16><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
+                                                        inv_out, H * W, C);
+  else if (inv_out != nullptr)
+    gn_apply_kernel<true, 32><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
+                                                        inv_out, H * W, C);
+  else if (residual)
+    gn_apply_kernel<true, 0><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
+                                                       nullptr, H * W, C);
   else
-    gn_apply_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride,
-                                                                   rr, yr, H * W, C);
+    gn_apply_kernel<false, 0><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
+                                                        nullptr, H * W, C);
   SRGD_LAUNCH_OK("gn_apply_kernel");
   count_launch();
   return SRGD_OK;

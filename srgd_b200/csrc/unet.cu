@@ -294,7 +294,7 @@ struct Fwd {
   void conv_gn(const void* a0, int c0, const void* a1, int c1, int H, int W, const void* w, const float* bias, int cout,
                void* out, float* stats) {
     const int mt = tile_geom(B, H, W).m_tiles;
-    float* part = reinterpret_cast<float*>(alloc((size_t)mt * 4 * 8 * 2 * sizeof(float)));
+    float* part = reinterpret_cast<float*>(alloc((size_t)mt * 8 * 8 * 2 * sizeof(float)));
     conv(a0, c0, a1, c1, H, W, 3, w, bias, cout, out, part, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC);
     if (!dry && ok()) {
       if (conv_impl & 3) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
@@ -304,14 +304,15 @@ struct Fwd {
   }
 
   // ResnetBlock (model.py:261-285).  Consumes nothing; returns a fresh [B][H][W][cout] buffer.
-  void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W) {
+  // inv_out (optional): receives 1/||row|| of the block output for the attention block that follows.
+  void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr) {
     const size_t M = (size_t)B * H * W;
     void* c1 = alloc(M * r.cout * 2);
     float* stats = reinterpret_cast<float*>(alloc((size_t)B * 8 * 2 * sizeof(float)));
     conv_gn(xa, r.cin0, xb, r.cin1, H, W, r.c1_w, r.c1_b, r.cout, c1, stats);
     if (!dry && ok())
-      run(srgd_groupnorm_apply(c1, B, stats, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, B, H, W, r.cout,
-                               st));
+      run(srgd_groupnorm_apply(c1, B, stats, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, nullptr, B, H, W,
+                               r.cout, st));
     void* c2 = alloc(M * r.cout * 2);
     conv_gn(c1, r.cout, nullptr, 0, H, W, r.c2_w, r.c2_b, r.cout, c2, stats);
     ar.release(c1);
@@ -324,7 +325,7 @@ struct Fwd {
       resid = rbuf;
     }
     if (!dry && ok())
-      run(srgd_groupnorm_apply(c2, B, stats, r.n2_g, r.n2_b, nullptr, 0, resid, c2, B, H, W, r.cout, st));
+      run(srgd_groupnorm_apply(c2, B, stats, r.n2_g, r.n2_b, nullptr, 0, resid, c2, inv_out, B, H, W, r.cout, st));
     ar.release(rbuf);
     ar.release(stats);
     tap(r.name, c2, M * r.cout * 2);
@@ -332,7 +333,13 @@ struct Fwd {
   }
 
   // attn(x) + x  (model.py:703, 709, 718).  Returns a fresh buffer.
-  void* attention(const AttnP& a, const void* x, int H, int W) {
+  // true if the resblock feeding this attention block should emit the per-pixel 1/||x|| (fused-LA path, C <= 256)
+  bool wants_inv(const AttnP& a, int H, int W) const {
+    return !a.full && !(conv_impl & 1) && srgd_linear_attention_block_supported(H * W, a.C, u.cfg.heads) &&
+           (a.C == 128 || a.C == 256) && (H * W) % 4 == 0;
+  }
+
+  void* attention(const AttnP& a, const void* x, int H, int W, const float* inv_in = nullptr) {
     const size_t M = (size_t)B * H * W;
     const int hid = u.hidden;
     if (!a.full && !(conv_impl & 1) && srgd_linear_attention_block_supported(H * W, a.C, u.cfg.heads)) {
@@ -341,8 +348,8 @@ struct Fwd {
       void* lws = alloc(wsb);
       void* out = alloc(M * a.C * 2);
       if (!dry && ok())
-        run(srgd_linear_attention_block(x, a.qkv_w, a.out_w, a.out_b, a.out_g, out, B, H * W, a.C, u.cfg.heads, lws,
-                                        wsb, st));
+        run(srgd_linear_attention_block(x, inv_in, a.qkv_w, a.out_w, a.out_b, a.out_g, out, B, H * W, a.C, u.cfg.heads,
+                                        lws, wsb, st));
       ar.release(lws);
       tap(a.name, out, M * a.C * 2);
       return out;
@@ -459,9 +466,11 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
     void* a = f.resblock(s.r0, xcur, nullptr, h, w);
     if (xcur != r) ar.release(xcur);
     skips.push_back(a); skip_c.push_back(s.r0.cout);
-    void* b2 = f.resblock(s.r1, a, nullptr, h, w);
-    void* at = f.attention(s.attn, b2, h, w);
+    float* inv = f.wants_inv(s.attn, h, w) ? reinterpret_cast<float*>(f.alloc((size_t)B * h * w * sizeof(float))) : nullptr;
+    void* b2 = f.resblock(s.r1, a, nullptr, h, w, inv);
+    void* at = f.attention(s.attn, b2, h, w, inv);
     ar.release(b2);
+    ar.release(inv);
     skips.push_back(at); skip_c.push_back(s.attn.C);
     if (!s.last) {
       xcur = f.downsample(s.resample, at, h, w);
@@ -489,10 +498,12 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
     void* a = f.resblock(s.r0, xcur, sk, h, w);
     ar.release(xcur); ar.release(sk);
     sk = skips.back(); skips.pop_back(); skip_c.pop_back();
-    void* b2 = f.resblock(s.r1, a, sk, h, w);
+    float* inv = f.wants_inv(s.attn, h, w) ? reinterpret_cast<float*>(f.alloc((size_t)B * h * w * sizeof(float))) : nullptr;
+    void* b2 = f.resblock(s.r1, a, sk, h, w, inv);
     ar.release(a); ar.release(sk);
-    void* at = f.attention(s.attn, b2, h, w);
+    void* at = f.attention(s.attn, b2, h, w, inv);
     ar.release(b2);
+    ar.release(inv);
     if (!s.last) {                                                      // PixelShuffleUpsample (model.py:70-98)
       const int cq = s.resample.cout / 4;
       xcur = f.alloc((size_t)B * (2 * h) * (2 * w) * cq * 2);

@@ -219,7 +219,7 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     ss = torch.randn(B, 2 * C + 7, generator=g) * 0.3             # row stride != 2C on purpose
     resid = G.bf16_round(torch.randn(B, C, H, W, generator=g))
     mt = lib.srgd_conv_m_tiles(B, H, W)
-    part = torch.full((mt * 4 * 8 * 2,), float("nan"), device="cuda")
+    part = torch.full((mt * 8 * 8 * 2,), float("nan"), device="cuda")
     out = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
     d = G.plain_conv_desc([G.nhwc_bf16(x)], G.pack_conv_weight(w), B, H, W, C, 3, out, bias=bias.cuda(),
                           gn_partials=part)
@@ -241,11 +241,16 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     y = F.group_norm(conv_b, 8, gamma, beta, eps=1e-5)
     y = F.silu(y * (scale[:, :, None, None] + 1) + shift[:, :, None, None]) + resid
     yd = torch.empty_like(out)
+    want_inv = C in (128, 256) and (H * W) % 4 == 0                          # fused RMSNorm statistic (model.py:207)
+    inv = torch.full((B * H * W,), float("nan"), device="cuda") if want_inv else None
     _lib.check(lib.srgd_groupnorm_apply(G.P(out), B, G.P(stats), G.P(gamma.cuda()), G.P(beta.cuda()),
-                                        G.P(ss.cuda()), 2 * C + 7, G.P(G.nhwc_bf16(resid)), G.P(yd),
+                                        G.P(ss.cuda()), 2 * C + 7, G.P(G.nhwc_bf16(resid)), G.P(yd), G.P(inv),
                                         B, H, W, C, G.stream()))
     torch.cuda.synchronize()
     assert rel_err(G.to_nchw_f32(yd), y) < 1.5e-2
+    if want_inv:
+        ref_inv = 1.0 / yd.float().reshape(B * H * W, C).norm(dim=1).clamp(min=1e-12)
+        torch.testing.assert_close(inv, ref_inv, rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("C", [64, 128, 256, 512, 1024])
@@ -313,7 +318,7 @@ def test_linear_attention_block_fused(lib, B, H, W, C):
     out = torch.empty_like(xd)
     wsb = lib.srgd_linear_attention_block_workspace(B, N, C, 4)
     ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
-    _lib.check(lib.srgd_linear_attention_block(G.P(xd), G.P(wq.cuda().bfloat16()), G.P(wo.cuda().bfloat16()),
+    _lib.check(lib.srgd_linear_attention_block(G.P(xd), None, G.P(wq.cuda().bfloat16()), G.P(wo.cuda().bfloat16()),
                                                G.P(sd["a.to_out.0.bias"].cuda()),
                                                G.P(sd["a.to_out.1.g"].reshape(-1).contiguous().cuda()), G.P(out), B, N, C, 4,
                                                G.P(ws), wsb, G.stream()), "linear_attention_block")
@@ -348,7 +353,7 @@ def test_linear_attention_block_reference_jumps(lib):
     out = torch.empty_like(xd)
     wsb = lib.srgd_linear_attention_block_workspace(B, N, C, 4)
     ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
-    _lib.check(lib.srgd_linear_attention_block(G.P(xd), G.P(sd["a.to_qkv.weight"].reshape(384, C).cuda().bfloat16()),
+    _lib.check(lib.srgd_linear_attention_block(G.P(xd), None, G.P(sd["a.to_qkv.weight"].reshape(384, C).cuda().bfloat16()),
                                                G.P(sd["a.to_out.0.weight"].reshape(C, 128).cuda().bfloat16()),
                                                G.P(sd["a.to_out.0.bias"].cuda()),
                                                G.P(sd["a.to_out.1.g"].reshape(-1).contiguous().cuda()), G.P(out), B, N, C, 4,
