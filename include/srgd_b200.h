@@ -145,6 +145,14 @@ int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const fl
                          const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
                          int32_t C, srgd_stream_t stream);
 
+/* Last ResnetBlock of the network fused with the final 1x1 conv (model.py:674-675, 724-725):
+ * eps[b][o][y][x] = final_b[o] + sum_c final_w[o][c] * ( SiLU(GN(x)*gamma+beta) + residual )[b][y][x][c],
+ * fp32 NCHW out, o < 3; the normalised activation itself is never stored.  C must be 128. */
+int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gamma, const float* beta,
+                               const void* residual, const float* final_w, const float* final_b,
+                               float* eps, int32_t B, int32_t H, int32_t W, int32_t C,
+                               srgd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * RMSNorm pieces (model.py:201-207)
  * ------------------------------------------------------------------------------------------ */
@@ -275,6 +283,12 @@ int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* la
 /* The individual records behind those sums, in launch order (valid after srgd_profile_end). */
 int srgd_profile_record_count(void);
 int srgd_profile_record(int index, int* kind, double* ms, double* flops, double* bytes);
+
+/* Test-only probe (not on the product path): D[128][128] = W[128][64] * X[shift:shift+128][64]^T with the B-operand
+ * descriptor's start address shifted by `shift` 128-byte rows inside a SWIZZLE_128B tile and base_offset field
+ * `base_off` -- the mechanism behind the conv kernels' horizontal-tap halo reuse (tests/test_gpu_kernels.py). */
+int srgd_debug_umma_shift(const void* w, const void* x, float* out, int32_t shift, int32_t base_off,
+                          srgd_stream_t stream);
 
 #ifdef __cplusplus
 }

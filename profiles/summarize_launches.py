@@ -49,6 +49,14 @@ def main():
         a["n"] += 1
         a["t"] += d.get("gpu__time_duration.sum", 0.0)
         a["by"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    if "--json" in sys.argv:
+        import json
+        out = sys.argv[sys.argv.index("--json") + 1]
+        json.dump({"source": path, "note": "ncu launch list, one bench step (cold-cache, serialised): compare shares",
+                   "total_ms": total / 1e3,
+                   "kernels": {k: {"launches": a["n"], "ms": a["t"] / 1e3, "share": a["t"] / total,
+                                   "dram_bytes": a["by"], "dram_bytes_per_launch": a["by"] / a["n"]}
+                               for k, a in agg.items()}}, open(out, "w"), indent=1)
     print(f"{len(L)} launches, {total / 1e3:.3f} ms total (serialised, cold-cache)")
     print(f"{'kernel':60s} {'n':>4s} {'ms':>8s} {'share':>6s} {'dram GB':>8s} {'GB/s':>7s}")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["t"]):

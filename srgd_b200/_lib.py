@@ -71,6 +71,7 @@ SIGNATURES = {
     "srgd_groupnorm_finalize": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_groupnorm_stats": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_groupnorm_apply": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "srgd_groupnorm_apply_final": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_pixel_inv_norm": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "srgd_rmsnorm_residual": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "srgd_linear_attention_workspace": (_SZ, [_I32, _I32, _I32]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "srgd_profile_end": (C.c_int, []),
     "srgd_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int)]),
+    "srgd_debug_umma_shift": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "srgd_profile_record_count": (C.c_int, []),
     "srgd_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),

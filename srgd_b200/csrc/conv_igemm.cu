@@ -325,19 +325,30 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // through a 32 KiB shared-memory staging tile and writes fully coalesced 256-byte NHWC rows.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTN = 256;                     // pixels per tile (two sub-tiles of 128)
-constexpr int kTStages = 4;
+// HALO variant (3x3 convs on W %% 256 == 0 images, one image-row segment of 256 pixels per tile): a pipeline stage is
+// one (source, 64-channel block, dy) "row stage": the 258-pixel row segment x0-1 .. x0+256 is fetched ONCE and the
+// three horizontal taps are three tcgen05.mma operand descriptors whose start address is shifted by 0 / 1 / 2
+// rows of 128 bytes inside the swizzled tile (the swizzle is a function of the absolute shared-memory address, so a
+// row-shifted start needs no descriptor change: tests/gpu_probe_umma_shift.py).  The plain variant re-reads every
+// activation nine times from L2 (48 KB per 512 MMA clocks and SM, 2/3 of it unique data) and was L2-bound at ~60 %
+// tensor-active on the 128->128 convs; this one moves 82 KB per 1536 clocks.
+template <bool HALO>
 struct ConvSmemT {
-  static constexpr int kWBytes = 128 * kBK * 2;            // weights: A operand, 16 KiB
-  static constexpr int kXBytes = kTN * kBK * 2;            // activations: B operand, 32 KiB
-  static constexpr int kStageBytes = kWBytes + kXBytes;    // 48 KiB
-  static constexpr int kStagingOffset = kTStages * kStageBytes;
-  static constexpr int kStagingBytes = 128 * 128 * 2;      // [128 pixels][128 ch] bf16
+  static constexpr int kStages = HALO ? 2 : 4;
+  static constexpr int kWBytes = (HALO ? 3 : 1) * 128 * kBK * 2;    // weights: A operand, 16 KiB per tap
+  static constexpr int kXBytes = HALO ? 33 * 1024 : kTN * kBK * 2;  // activations: B operand (258 rows padded / 256)
+  static constexpr int kXTxBytes = HALO ? 258 * 128 : kTN * kBK * 2;
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  static constexpr int kStagingOffset = kStages * kStageBytes;
+  static constexpr int kStagingBytes = 128 * 128 * 2;      // 2 halves x [64 pixels][128 ch] bf16
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kTStages + 4) * 8 + 16 + 1024;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
+template <bool HALO>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_constant__ ConvKernelParams p) {
-  using L = ConvSmemT;
+  using L = ConvSmemT<HALO>;
+  constexpr int kTStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   bf16* staging = reinterpret_cast<bf16*>(smem + L::kStagingOffset);
@@ -353,6 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
 
   if (warp == kTmaWarp && lane == 0) {
     for (int i = 0; i < p.n_src; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
+    if (HALO)
+      for (int i = 0; i < p.n_src; ++i) ptx::prefetch_tmap(&p.a_maps[2 + i]);
     ptx::prefetch_tmap(&p.w_map);
   }
   if (warp == kMmaWarp && lane == 0) {
@@ -395,20 +408,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
         y0[s] = ((st / p.tiles_x) % p.tiles_y) << p.th_log2;
         b0[s] = (st / tiles_xy) << tn_log2;
       }
-      for (int ph = 0; ph < p.n_phase; ++ph) {
-        const CUtensorMap* amap = &p.a_maps[p.ph_src[ph]];
-        const int dx = p.ph_dx[ph], dy = p.ph_dy[ph];
-        const int kblk0 = p.ph_kblk[ph];
-        const int ncb = p.ph_cblocks[ph];
-        for (int cb = 0; cb < ncb; ++cb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* w_dst = smem + stage * L::kStageBytes;
-          uint8_t* x_dst = w_dst + L::kWBytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          ptx::tma_load_2d(w_dst, &p.w_map, &full_bar[stage], (kblk0 + cb) * kBK, n_tile * 128);
-          ptx::tma_load_4d(x_dst, amap, &full_bar[stage], cb * kBK, x0[0] + dx, y0[0] + dy, b0[0]);
-          ptx::tma_load_4d(x_dst + kABytes, amap, &full_bar[stage], cb * kBK, x0[1] + dx, y0[1] + dy, b0[1]);
-          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+      if (HALO) {
+        // phases are ordered (ky, kx, source) (checked by the launcher); sub-tile 1 continues sub-tile 0's row
+        for (int src = 0; src < p.n_src; ++src) {
+          const int ncb = p.ph_cblocks[src];
+          for (int cb = 0; cb < ncb; ++cb) {
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* w_dst = smem + stage * L::kStageBytes;
+              uint8_t* x_dst = w_dst + L::kWBytes;
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kWBytes + L::kXTxBytes);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi)
+                ptx::tma_load_2d(w_dst + dxi * 16384, &p.w_map, &full_bar[stage],
+                                 (p.ph_kblk[(dyi * 3 + dxi) * p.n_src + src] + cb) * kBK, n_tile * 128);
+              ptx::tma_load_4d(x_dst, &p.a_maps[src], &full_bar[stage], cb * kBK, x0[0] - 1, y0[0] + dyi - 1, b0[0]);
+              ptx::tma_load_4d(x_dst + 256 * 128, &p.a_maps[2 + src], &full_bar[stage], cb * kBK, x0[0] + 255,
+                               y0[0] + dyi - 1, b0[0]);
+              if (++stage == kTStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else {
+        for (int ph = 0; ph < p.n_phase; ++ph) {
+          const CUtensorMap* amap = &p.a_maps[p.ph_src[ph]];
+          const int dx = p.ph_dx[ph], dy = p.ph_dy[ph];
+          const int kblk0 = p.ph_kblk[ph];
+          const int ncb = p.ph_cblocks[ph];
+          for (int cb = 0; cb < ncb; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* w_dst = smem + stage * L::kStageBytes;
+            uint8_t* x_dst = w_dst + L::kWBytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            ptx::tma_load_2d(w_dst, &p.w_map, &full_bar[stage], (kblk0 + cb) * kBK, n_tile * 128);
+            ptx::tma_load_4d(x_dst, amap, &full_bar[stage], cb * kBK, x0[0] + dx, y0[0] + dy, b0[0]);
+            ptx::tma_load_4d(x_dst + kABytes, amap, &full_bar[stage], cb * kBK, x0[1] + dx, y0[1] + dy, b0[1]);
+            if (++stage == kTStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -423,17 +459,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kTN;
-      for (int kb = 0; kb < p.total_kblocks; ++kb) {
+      const int n_stages = HALO ? p.total_kblocks / 3 : p.total_kblocks;
+      for (int kb = 0; kb < n_stages; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t w_addr = ptx::smem_u32(smem + stage * L::kStageBytes);
-        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(w_addr);                 // weights  [128 ch][64 k]
-        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(w_addr + L::kWBytes);    // pixels   [256 px][64 k]
+        if (HALO) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            const uint64_t a_desc = ptx::make_sw128_kmajor_desc(w_addr + dxi * 16384);            // tap weights
+            const uint64_t b_desc = ptx::make_sw128_kmajor_desc(w_addr + L::kWBytes + dxi * 128);  // row-shifted pixels
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | dxi | k) != 0 ? 1u : 0u);
+          }
+        } else {
+          const uint64_t a_desc = ptx::make_sw128_kmajor_desc(w_addr);                 // weights  [128 ch][64 k]
+          const uint64_t b_desc = ptx::make_sw128_kmajor_desc(w_addr + L::kWBytes);    // pixels   [256 px][64 k]
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
         ptx::umma_commit(&empty_bar[stage]);
-        if (kb == p.total_kblocks - 1) ptx::umma_commit(&tfull_bar[acc]);
+        if (kb == n_stages - 1) ptx::umma_commit(&tfull_bar[acc]);
         if (++stage == kTStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -708,15 +756,16 @@ static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
   return SRGD_OK;
 }
 
+template <bool HALO>
 static int launch_igemm_t(const ConvKernelParams& kp, cudaStream_t st) {
+  using L = ConvSmemT<HALO>;
   static bool configured = false;
   if (!configured) {
-    SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      ConvSmemT::kTotal));
+    SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_t_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
-  conv_igemm_t_kernel<<<grid, kThreads, ConvSmemT::kTotal, st>>>(kp);
+  conv_igemm_t_kernel<HALO><<<grid, kThreads, L::kTotal, st>>>(kp);
   SRGD_LAUNCH_OK("conv_igemm_t_kernel");
   count_launch();
   return SRGD_OK;
@@ -759,6 +808,16 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
       SRGD_REQUIRE(BN <= 256 && d->Cout % BN == 0, "conv: cannot tile Cout=%d for GroupNorm partials", d->Cout);
   }
   if (swapped) BN = 128;
+  // halo-reuse variant: plain 3x3 window over 1 or 2 same-sized sources, phases ordered (ky, kx, source), tiles that
+  // are image-row segments and pair up inside a row
+  bool halo = swapped && d->n_src <= 2 && d->n_phase == 9 * d->n_src && g.tw_log2 == 7 && g.th_log2 == 0 &&
+              d->Wo % 256 == 0 && !(force != nullptr && force[0] == 't');
+  for (int i = 0; halo && i < d->n_phase; ++i) {
+    const int tap = i / d->n_src, src = i % d->n_src;
+    const srgd_conv_phase& ph = d->phases[i];
+    halo = ph.src == src && ph.dy == tap / 3 - 1 && ph.dx == tap % 3 - 1 && d->srcs[src].H == d->Ho &&
+           d->srcs[src].W == d->Wo;
+  }
 
   ConvKernelParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -767,7 +826,7 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
     const srgd_conv_src& s = d->srcs[i];
     const cuuint64_t gdim[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)d->B};
     const cuuint64_t gstr[3] = {(cuuint64_t)s.sx * 2, (cuuint64_t)s.sy * 2, (cuuint64_t)s.sb * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)kBK, 1u << g.tw_log2, 1u << g.th_log2, 1u << g.tn_log2};
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, halo ? 256u : 1u << g.tw_log2, 1u << g.th_log2, 1u << g.tn_log2};
     CUresult r = encode(&kp.a_maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.ptr), gdim, gstr, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -775,6 +834,21 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
       set_error("conv: cuTensorMapEncodeTiled(src %d: C=%d W=%d H=%d B=%d sx=%lld sy=%lld sb=%lld) failed with %d", i,
                 s.C, s.W, s.H, d->B, (long long)s.sx, (long long)s.sy, (long long)s.sb, (int)r);
       return SRGD_E_CUDA;
+    }
+  }
+  if (halo) {                                               // 2-pixel tail boxes of the 258-pixel row segments
+    for (int i = 0; i < d->n_src; ++i) {
+      const srgd_conv_src& s = d->srcs[i];
+      const cuuint64_t gdim[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)d->B};
+      const cuuint64_t gstr[3] = {(cuuint64_t)s.sx * 2, (cuuint64_t)s.sy * 2, (cuuint64_t)s.sb * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)kBK, 2u, 1u, 1u};
+      CUresult r = encode(&kp.a_maps[2 + i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.ptr), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("conv: cuTensorMapEncodeTiled(halo tail, src %d) failed with %d", i, (int)r);
+        return SRGD_E_CUDA;
+      }
     }
   }
   {
@@ -819,7 +893,7 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   const double M = (double)d->B * d->Ho * d->Wo;
   ProfScope prof(SRGD_PK_CONV, 2.0 * M * d->Cout * total_kb * kBK,
                  2.0 * (M * total_kb * kBK + (double)d->Cout * d->Ktot + M * d->Cout), st);
-  if (swapped) return launch_igemm_t(kp, st);
+  if (swapped) return halo ? launch_igemm_t<true>(kp, st) : launch_igemm_t<false>(kp, st);
   switch (BN) {
     case 64: return launch_igemm<64, 8>(kp, st);
     case 128: return launch_igemm<128, 6>(kp, st);

@@ -269,30 +269,53 @@ __global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restrict__ part, const bf16* __restrict__ wout,
                                                           bf16* __restrict__ mb, int splits, int C) {
-  extern __shared__ uint8_t merge_smem[];                  // Wout[:, h*32:(h+1)*32] as bf16 [C][32]
+  extern __shared__ uint8_t merge_smem[];                  // Wout[:, h*32:(h+1)*32] as bf16 [C][32] | float [4][34][32]
   const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
   const int d = threadIdx.x & 31, cq = threadIdx.x >> 5;
   uint4* wsm = reinterpret_cast<uint4*>(merge_smem);
+  float* red = reinterpret_cast<float*>(merge_smem + (size_t)C * 64);
   for (int i = threadIdx.x; i < C * 4; i += 128)           // 4 x 16 B per output channel
     wsm[i] = __ldg(reinterpret_cast<const uint4*>(wout + (int64_t)(i >> 2) * kLfHid + h * 32) + (i & 3));
+  // each warp (cq) folds every fourth split record; the four partial results are combined through shared memory
   const float* base = part + (int64_t)b * splits * (34 * kLfHid) + h * 32 + d;
   const int64_t sstride = 34 * kLfHid;
   float m = -INFINITY;
-  for (int s = 0; s < splits; ++s) m = fmaxf(m, base[s * sstride]);
+  for (int s = cq; s < splits; s += 4) m = fmaxf(m, __ldg(base + s * sstride));
   float z = 0.f, acc[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-  for (int s = 0; s < splits; ++s) {
+  for (int s = cq; s < splits; s += 4) {
     const float* src = base + s * sstride;
-    const float w = __expf(src[0] - m);
-    z += w * src[kLfHid];
+    const float ms = __ldg(src);
+    const float w = (ms == -INFINITY) ? 0.f : __expf(ms - m);   // empty records (CTA without tiles) carry m = -inf
+    z = fmaf(w, __ldg(src + kLfHid), z);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, src[(2 + e) * kLfHid], acc[e]);
+    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, __ldg(src + (2 + e) * kLfHid), acc[e]);
+  }
+  float* mine = red + (cq * 34) * 32 + d;
+  mine[0] = m;
+  mine[32] = z;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) mine[(2 + e) * 32] = acc[e];
+  __syncthreads();
+  float mm = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mm = fmaxf(mm, red[(k * 34) * 32 + d]);
+  z = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float* r = red + (k * 34) * 32 + d;
+    const float mk = r[0];
+    const float w = (mk == -INFINITY) ? 0.f : __expf(mk - mm);
+    z = fmaf(w, r[32], z);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = fmaf(w, r[(2 + e) * 32], acc[e]);
   }
   const float inv = kLfQScale / z;
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] *= inv;
-  __syncthreads();
   const int cper = C >> 2;
 #pragma unroll 2
   for (int c = cq * cper; c < (cq + 1) * cper; ++c) {
@@ -644,7 +667,7 @@ extern "C" int srgd_linear_attention_block(const void* x, const float* inv_norm,
   }
   la_ctx_kernel<<<dim3(splits, B), 320, LaCtxSmem::kTotal, st>>>(ap);
   SRGD_LAUNCH_OK("la_ctx_kernel");
-  la_merge_mb_kernel<<<B * 4, 128, (size_t)C * 64, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, splits, C);
+  la_merge_mb_kernel<<<B * 4, 128, (size_t)C * 64 + 4 * 34 * 32 * 4, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, splits, C);
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
   count_launch(2);
 

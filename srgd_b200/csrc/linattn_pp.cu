@@ -641,7 +641,7 @@ int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, cons
   }
   la_ctx_pp_kernel<<<dim3(splits, B), 576, LaCtxPpSmem::kTotal, st>>>(ap);
   SRGD_LAUNCH_OK("la_ctx_pp_kernel");
-  la_merge_mb_kernel<<<B * 4, 128, 128 * 64, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, 2 * splits, 128);
+  la_merge_mb_kernel<<<B * 4, 128, 128 * 64 + 4 * 34 * 32 * 4, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, 2 * splits, 128);
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
 
   LaOutPpParams bp;

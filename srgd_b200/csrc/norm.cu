@@ -106,16 +106,22 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 // INV_LANES > 0: additionally emit inv_out[pixel] = 1 / max(||y[pixel,:]||_2, 1e-12) of the bf16-rounded output row
 // (the RMSNorm of the attention block that consumes y, model.py:207); the C/8 = INV_LANES threads of a pixel are
 // consecutive lanes of one warp.
-template <bool HAS_RES, int INV_LANES>
+// FINAL: y is not stored; instead the U-Net's final 1x1 conv C -> 3 (model.py:675, 725) is evaluated on the fp32
+// values and written as fp32 NCHW eps (fin_w [3][C], fin_b [3]); C = 128, the 16 threads of a pixel reduce by shuffle.
+template <bool HAS_RES, int INV_LANES, bool FINAL>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
                                                        const bf16* residual, bf16* y, float* __restrict__ inv_out,
-                                                       int HW, int C) {
-  extern __shared__ float sm[];                          // A[C] | B[C]
+                                                       const float* __restrict__ fin_w, const float* __restrict__ fin_b,
+                                                       float* __restrict__ eps, int HW, int C) {
+  extern __shared__ float sm[];                          // A[C] | B[C] | (FINAL: fin_w[3][C])
   float* sA = sm;
   float* sB = sm + C;
+  float* sW = sm + 2 * C;
+  if (FINAL)
+    for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sW[c] = fin_w[c];
   const int b = blockIdx.y;
   const int bs = b % Bx;
   const int G = C / kGroups;
@@ -170,6 +176,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
         unpack8(rv[u], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (FINAL) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          d0 = fmaf(f[j], sW[c0 + j], d0);
+          d1 = fmaf(f[j], sW[C + c0 + j], d1);
+          d2 = fmaf(f[j], sW[2 * C + c0 + j], d2);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if ((threadIdx.x & 15) == 0) {
+          const int64_t pix = iu / vec_per_pix;
+          float* e0 = eps + (int64_t)b * 3 * HW + pix;
+          e0[0] = d0 + fin_b[0];
+          e0[HW] = d1 + fin_b[1];
+          e0[2 * (int64_t)HW] = d2 + fin_b[2];
+        }
+        continue;
       }
       const uint4 packed = pack8(f);
       st_stream(ys + iu * 8, packed);
@@ -320,18 +349,41 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
                "groupnorm_apply: inv_out needs the residual variant, C in {128, 256} and H*W %% 4 == 0");
   cudaStream_t cst = as_stream(stream);
   if (inv_out != nullptr && C == 128)
-    gn_apply_kernel<true, 16><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
-                                                        inv_out, H * W, C);
+    gn_apply_kernel<true, 16, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
+                                                               yr, inv_out, nullptr, nullptr, nullptr, H * W, C);
   else if (inv_out != nullptr)
-    gn_apply_kernel<true, 32><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
-                                                        inv_out, H * W, C);
+    gn_apply_kernel<true, 32, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
+                                                               yr, inv_out, nullptr, nullptr, nullptr, H * W, C);
   else if (residual)
-    gn_apply_kernel<true, 0><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
-                                                       nullptr, H * W, C);
+    gn_apply_kernel<true, 0, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
+                                                              yr, nullptr, nullptr, nullptr, nullptr, H * W, C);
   else
-    gn_apply_kernel<false, 0><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr, yr,
-                                                        nullptr, H * W, C);
+    gn_apply_kernel<false, 0, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
+                                                               yr, nullptr, nullptr, nullptr, nullptr, H * W, C);
   SRGD_LAUNCH_OK("gn_apply_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gamma, const float* beta,
+                                          const void* residual, const float* final_w, const float* final_b,
+                                          float* eps, int32_t B, int32_t H, int32_t W, int32_t C,
+                                          srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(x && stats && gamma && beta && residual && final_w && final_b && eps, "groupnorm_apply_final: null argument");
+  SRGD_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && C == 128 && (H * W) % 2 == 0,
+               "groupnorm_apply_final: needs C == 128 and an even pixel count (B=%d H=%d W=%d C=%d)", B, H, W, C);
+  const int64_t total = (int64_t)H * W * (C / 8);
+  int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
+  if ((int64_t)gx * B > (int64_t)sm_count() * 16) gx = (sm_count() * 16 + B - 1) / B;
+  dim3 grid(gx, B);
+  const size_t smem = (size_t)C * 5 * sizeof(float);
+  ProfScope prof(SRGD_PK_GN_APPLY, 2.0 * B * H * W * C * 3, (double)B * H * W * (C * 4.0 + 12.0), as_stream(stream));
+  gn_apply_kernel<true, 0, true><<<grid, 256, smem, as_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0, reinterpret_cast<const bf16*>(residual), nullptr,
+      nullptr, final_w, final_b, eps, H * W, C);
+  SRGD_LAUNCH_OK("gn_apply_kernel(final)");
   count_launch();
   return SRGD_OK;
 }

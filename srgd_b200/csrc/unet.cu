@@ -305,7 +305,10 @@ struct Fwd {
 
   // ResnetBlock (model.py:261-285).  Consumes nothing; returns a fresh [B][H][W][cout] buffer.
   // inv_out (optional): receives 1/||row|| of the block output for the attention block that follows.
-  void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr) {
+  // eps_out (optional, last block of the network only): the final 1x1 conv is fused into the second GroupNorm pass
+  // (srgd_groupnorm_apply_final); the block output is then not materialised and nullptr is returned.
+  void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr,
+                 float* eps_out = nullptr) {
     const size_t M = (size_t)B * H * W;
     void* c1 = alloc(M * r.cout * 2);
     float* stats = reinterpret_cast<float*>(alloc((size_t)B * 8 * 2 * sizeof(float)));
@@ -323,6 +326,15 @@ struct Fwd {
       conv(xa, r.cin0, xb, r.cin1, H, W, 1, r.res_w, r.res_b, r.cout, rbuf, nullptr, nullptr, nullptr, 0,
            SRGD_OUT_BF16_NHWC);
       resid = rbuf;
+    }
+    if (eps_out != nullptr) {
+      if (!dry && ok())
+        run(srgd_groupnorm_apply_final(c2, stats, r.n2_g, r.n2_b, resid, u.final_w, u.final_b, eps_out, B, H, W, r.cout,
+                                       st));
+      ar.release(rbuf);
+      ar.release(stats);
+      ar.release(c2);
+      return nullptr;
     }
     if (!dry && ok())
       run(srgd_groupnorm_apply(c2, B, stats, r.n2_g, r.n2_b, nullptr, 0, resid, c2, inv_out, B, H, W, r.cout, st));
@@ -520,11 +532,14 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
     ar.release(at);
   }
   // ---- head (model.py:722-725) ----
-  void* fr = f.resblock(u.final_res, xcur, r, h, w);
+  const bool fuse_final = !(conv_impl & 1) && u.taps.empty() && dim == 128 && c.channels == 3 && (h * w) % 2 == 0;
+  void* fr = f.resblock(u.final_res, xcur, r, h, w, nullptr, fuse_final ? (dry ? reinterpret_cast<float*>(1) : eps) : nullptr);
   ar.release(xcur);
   ar.release(r);
-  if (!dry && f.ok()) f.run(srgd_final_conv(fr, u.final_w, u.final_b, eps, B, h, w, dim, c.channels, st));
-  ar.release(fr);
+  if (!fuse_final) {
+    if (!dry && f.ok()) f.run(srgd_final_conv(fr, u.final_w, u.final_b, eps, B, h, w, dim, c.channels, st));
+    ar.release(fr);
+  }
   ar.release(t);
   ar.release(ss);
   return f.rc;

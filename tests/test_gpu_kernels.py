@@ -92,15 +92,19 @@ CONV_CASES = [
     (1, 32, 32, [1024, 512], 1024, 1),    # long-K 1x1 over a concat
     (1, 24, 40, [128], 128, 3),           # odd number of pixel tiles (channels-as-M pairs them)
     (5, 16, 16, [128], 384, 1),
+    (1, 6, 256, [128], 128, 3),           # W % 256 == 0: halo-reuse variant (row-shifted tcgen05 operand descriptors)
+    (2, 3, 512, [64, 128], 128, 3),       # halo reuse over a concat, two 256-pixel tiles per row
+    (1, 2, 256, [64], 384, 3),            # halo reuse, three 128-channel slabs
 ]
 
 
-@pytest.fixture(params=["auto", "n"])
+@pytest.fixture(params=["auto", "n", "t"])
 def conv_variant(request):
-    """auto: channels-as-M kernel for 128-wide Cout slabs; n: force the pixels-as-M kernel."""
+    """auto: channels-as-M kernel for 128-wide Cout slabs (halo-reuse variant where it applies); n: force the
+    pixels-as-M kernel; t: channels-as-M without halo reuse."""
     import os
-    if request.param == "n":
-        os.environ["SRGD_CONV_VARIANT"] = "n"
+    if request.param != "auto":
+        os.environ["SRGD_CONV_VARIANT"] = request.param
     yield request.param
     os.environ.pop("SRGD_CONV_VARIANT", None)
 
@@ -108,7 +112,7 @@ def conv_variant(request):
 @pytest.mark.parametrize("B,H,W,cins,Cout,ks", CONV_CASES)
 @pytest.mark.parametrize("direct", [False, True])
 def test_conv_matches_torch(lib, conv_variant, B, H, W, cins, Cout, ks, direct):
-    if direct and conv_variant == "n":
+    if direct and conv_variant != "auto":
         pytest.skip("direct path has no variants")
     g = torch.Generator().manual_seed(B * 1000 + H + Cout)
     xs = [G.bf16_round(torch.randn(B, c, H, W, generator=g)) for c in cins]
@@ -207,7 +211,7 @@ def test_init_conv_pack_and_7tap(lib):
 # ------------------------------------------------------------------------------------------------
 # GroupNorm / RMSNorm
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64), (2, 4, 256, 128)])
 def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     g = torch.Generator().manual_seed(C + H)
     Cin = 128
@@ -251,6 +255,26 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     if want_inv:
         ref_inv = 1.0 / yd.float().reshape(B * H * W, C).norm(dim=1).clamp(min=1e-12)
         torch.testing.assert_close(inv, ref_inv, rtol=1e-5, atol=1e-7)
+
+
+def test_groupnorm_apply_final_fused_conv(lib):
+    """Last GroupNorm pass + residual fused with the final 1x1 conv 128 -> 3 (model.py:674-675, 724-725)."""
+    g = torch.Generator().manual_seed(9)
+    B, H, W, C = 2, 16, 24, 128
+    x = G.bf16_round(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.2)
+    res = G.bf16_round(torch.randn(B, C, H, W, generator=g))
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    w3, b3 = torch.randn(3, C, generator=g) / math.sqrt(C), torch.randn(3, generator=g) * 0.1
+    xd = G.nhwc_bf16(x)
+    stats = torch.empty(B * 8 * 2, device="cuda")
+    _lib.check(lib.srgd_groupnorm_stats(G.P(xd), G.P(stats), B, H, W, C, G.stream()))
+    eps = torch.full((B, 3, H, W), float("nan"), device="cuda")
+    _lib.check(lib.srgd_groupnorm_apply_final(G.P(xd), G.P(stats), G.P(gamma.cuda()), G.P(beta.cuda()),
+                                              G.P(G.nhwc_bf16(res)), G.P(w3.cuda().contiguous()), G.P(b3.cuda()), G.P(eps),
+                                              B, H, W, C, G.stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.silu(F.group_norm(x, 8, gamma, beta, eps=1e-5)) + res, w3.reshape(3, C, 1, 1), b3)
+    assert rel_err(eps.cpu(), ref) < 5e-3
 
 
 @pytest.mark.parametrize("C", [64, 128, 256, 512, 1024])
