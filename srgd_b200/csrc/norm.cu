@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 // consecutive lanes of one warp.
 // FINAL: y is not stored; instead the U-Net's final 1x1 conv C -> 3 (model.py:675, 725) is evaluated on the fp32
 // values and written as fp32 NCHW eps (fin_w [3][C], fin_b [3]); C = 128, the 16 threads of a pixel reduce by shuffle.
-template <bool HAS_RES, int INV_LANES, bool FINAL>
+// REG: C/8 is a power of two <= 256, so a thread always meets the same 8 channels (every stride is a multiple of
+// 256 vectors) and keeps its affine coefficients -- and the final-conv weights -- in registers: no shared-memory
+// traffic and no block barrier.
+template <bool HAS_RES, int INV_LANES, bool FINAL, bool REG>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
@@ -116,31 +119,45 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
                                                        const bf16* residual, bf16* y, float* __restrict__ inv_out,
                                                        const float* __restrict__ fin_w, const float* __restrict__ fin_b,
                                                        float* __restrict__ eps, int HW, int C) {
-  extern __shared__ float sm[];                          // A[C] | B[C] | (FINAL: fin_w[3][C])
+  extern __shared__ float sm[];                          // !REG: A[C] | B[C] | (FINAL: fin_w[3][C])
   float* sA = sm;
   float* sB = sm + C;
   float* sW = sm + 2 * C;
-  if (FINAL)
-    for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sW[c] = fin_w[c];
   const int b = blockIdx.y;
   const int bs = b % Bx;
   const int G = C / kGroups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int vec_per_pix = C / 8;
+  float ra[8], rb[8], rw[24];
+  auto coef = [&](int c, float& a, float& bb) {
     const float mean = stats[(bs * kGroups + c / G) * 2];
     const float rstd = stats[(bs * kGroups + c / G) * 2 + 1];
-    float a = rstd * gamma[c];
-    float bb = beta[c] - mean * a;
+    a = rstd * gamma[c];
+    bb = beta[c] - mean * a;
     if (scale_shift != nullptr) {
       const float sc = scale_shift[(int64_t)b * ss_stride + c] + 1.0f;     // model.py:256
       const float sh = scale_shift[(int64_t)b * ss_stride + C + c];
       a *= sc;
       bb = bb * sc + sh;
     }
-    sA[c] = a;
-    sB[c] = bb;
+  };
+  if (REG) {
+    const int c0 = (int)(threadIdx.x % vec_per_pix) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) coef(c0 + j, ra[j], rb[j]);
+    if (FINAL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rw[j] = fin_w[c0 + j];
+        rw[8 + j] = fin_w[C + c0 + j];
+        rw[16 + j] = fin_w[2 * C + c0 + j];
+      }
+    }
+  } else {
+    if (FINAL)
+      for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sW[c] = fin_w[c];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) coef(c, sA[c], sB[c]);
+    __syncthreads();
   }
-  __syncthreads();
-  const int vec_per_pix = C / 8;
   const int64_t total = (int64_t)HW * vec_per_pix;
   const bf16* xs = x + (int64_t)bs * HW * C;
   const bf16* rs = HAS_RES ? residual + (int64_t)b * HW * C : nullptr;
@@ -164,12 +181,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
       const int c0 = (int)(iu % vec_per_pix) * 8;
       float f[8];
       unpack8(xv[u], f);
-      const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
-      f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y);
-      f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-      f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y);
-      f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+      if (REG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], ra[j], rb[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sA[c0 + j], sB[c0 + j]);
+      }
       silu2(f[0], f[1]); silu2(f[2], f[3]); silu2(f[4], f[5]); silu2(f[6], f[7]);
       if (HAS_RES) {
         float r[8];
@@ -181,9 +199,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          d0 = fmaf(f[j], sW[c0 + j], d0);
-          d1 = fmaf(f[j], sW[C + c0 + j], d1);
-          d2 = fmaf(f[j], sW[2 * C + c0 + j], d2);
+          d0 = fmaf(f[j], REG ? rw[j] : sW[c0 + j], d0);
+          d1 = fmaf(f[j], REG ? rw[8 + j] : sW[C + c0 + j], d1);
+          d2 = fmaf(f[j], REG ? rw[16 + j] : sW[2 * C + c0 + j], d2);
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
@@ -348,18 +366,19 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   SRGD_REQUIRE(inv_out == nullptr || (residual != nullptr && (C == 128 || C == 256) && (H * W) % 4 == 0),
                "groupnorm_apply: inv_out needs the residual variant, C in {128, 256} and H*W %% 4 == 0");
   cudaStream_t cst = as_stream(stream);
-  if (inv_out != nullptr && C == 128)
-    gn_apply_kernel<true, 16, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
-                                                               yr, inv_out, nullptr, nullptr, nullptr, H * W, C);
-  else if (inv_out != nullptr)
-    gn_apply_kernel<true, 32, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
-                                                               yr, inv_out, nullptr, nullptr, nullptr, H * W, C);
-  else if (residual)
-    gn_apply_kernel<true, 0, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
-                                                              yr, nullptr, nullptr, nullptr, nullptr, H * W, C);
-  else
-    gn_apply_kernel<false, 0, false><<<grid, 256, smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift, ss_stride, rr,
-                                                               yr, nullptr, nullptr, nullptr, nullptr, H * W, C);
+  const int vpp = C / 8;
+  const bool reg = (vpp & (vpp - 1)) == 0 && vpp <= 256;
+#define SRGD_GN_LAUNCH(RES, INV, R)                                                                              \
+  gn_apply_kernel<RES, INV, false, R><<<grid, 256, R ? 0 : smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift,  \
+                                                                       ss_stride, rr, yr, inv_out, nullptr,      \
+                                                                       nullptr, nullptr, H * W, C)
+  if (inv_out != nullptr && C == 128) SRGD_GN_LAUNCH(true, 16, true);
+  else if (inv_out != nullptr) SRGD_GN_LAUNCH(true, 32, true);
+  else if (residual && reg) SRGD_GN_LAUNCH(true, 0, true);
+  else if (residual) SRGD_GN_LAUNCH(true, 0, false);
+  else if (reg) SRGD_GN_LAUNCH(false, 0, true);
+  else SRGD_GN_LAUNCH(false, 0, false);
+#undef SRGD_GN_LAUNCH
   SRGD_LAUNCH_OK("gn_apply_kernel");
   count_launch();
   return SRGD_OK;
@@ -380,7 +399,8 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 5 * sizeof(float);
   ProfScope prof(SRGD_PK_GN_APPLY, 2.0 * B * H * W * C * 3, (double)B * H * W * (C * 4.0 + 12.0), as_stream(stream));
-  gn_apply_kernel<true, 0, true><<<grid, 256, smem, as_stream(stream)>>>(
+  (void)smem;
+  gn_apply_kernel<true, 0, true, true><<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0, reinterpret_cast<const bf16*>(residual), nullptr,
       nullptr, final_w, final_b, eps, H * W, C);
   SRGD_LAUNCH_OK("gn_apply_kernel(final)");
