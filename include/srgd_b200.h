@@ -74,6 +74,22 @@ int srgd_q_sample(const float* x_start, const float* noise, float* out, int64_t 
 /* final clamp(-1,1) and (x+1)/2 (model.py:3237-3238, 3404-3405). out may alias img. */
 int srgd_finalize_image(const float* img, float* out, int64_t n, srgd_stream_t stream);
 
+/* Tiled sampling orchestration (tiled_sample, model.py:3361-3396) on a fp32 [C][H][W] canvas (batch 1):
+ * gather up to SRGD_MAX_TILES_PER_CALL T x T tiles into a [n][C][T][T] minibatch (model.py:3364-3371),
+ * scatter results back (3377-3380), and replace the state outside the hull [y0,y1) x [x0,x1) of the
+ * shifted grid by sigma * noise (q_sample of zeros, 3392-3396).  Tile x offsets must be multiples of 4. */
+enum { SRGD_MAX_TILES_PER_CALL = 64 };
+typedef struct srgd_tile_coords {
+  int32_t n;
+  int32_t yx[SRGD_MAX_TILES_PER_CALL][2];   /* top-left (y, x) of each tile on the canvas */
+} srgd_tile_coords;
+int srgd_gather_tiles(const float* canvas, float* tiles, const srgd_tile_coords* tc, int32_t C, int32_t H,
+                      int32_t W, int32_t T, srgd_stream_t stream);
+int srgd_scatter_tiles(float* canvas, const float* tiles, const srgd_tile_coords* tc, int32_t C, int32_t H,
+                       int32_t W, int32_t T, srgd_stream_t stream);
+int srgd_renoise_outside(float* img, const float* noise, int32_t C, int32_t H, int32_t W, int32_t y0,
+                         int32_t y1, int32_t x0, int32_t x1, float sigma, srgd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM on tcgen05 tensor cores (nn.Conv2d call sites model.py:246, 271,
  * 300, 303, 341, 342, 109, 78, 647, 668, 583).  D[M=B*Ho*Wo, N=Cout] = sum over taps and input

@@ -27,6 +27,13 @@ class StepScalars(C.Structure):
                 ("noise_scale", C.c_float), ("guidance_scale", C.c_float), ("clip", C.c_int32)]
 
 
+SRGD_MAX_TILES_PER_CALL = 64
+
+
+class TileCoords(C.Structure):
+    _fields_ = [("n", C.c_int32), ("yx", (C.c_int32 * 2) * SRGD_MAX_TILES_PER_CALL)]
+
+
 class ConvSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sy", C.c_int64), ("sx", C.c_int64),
                 ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32)]
@@ -65,6 +72,9 @@ SIGNATURES = {
     "srgd_sampler_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(StepScalars), _P]),
     "srgd_q_sample": (C.c_int, [_P, _P, _P, _I64, C.c_float, C.c_float, _P]),
     "srgd_finalize_image": (C.c_int, [_P, _P, _I64, _P]),
+    "srgd_gather_tiles": (C.c_int, [_P, _P, C.POINTER(TileCoords), _I32, _I32, _I32, _I32, _P]),
+    "srgd_scatter_tiles": (C.c_int, [_P, _P, C.POINTER(TileCoords), _I32, _I32, _I32, _I32, _P]),
+    "srgd_renoise_outside": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P]),
     "srgd_conv_m_tiles": (C.c_int, [_I32, _I32, _I32]),
     "srgd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "srgd_conv_direct": (C.c_int, [C.POINTER(ConvDesc), _P]),

@@ -84,6 +84,37 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* img, float* 
   }
 }
 
+// ---- tiled sampling orchestration (model.py:3361-3396): batched tile gather / scatter, re-noise outside a hull ----
+// canvas fp32 [C][H][W] (batch 1, like the reference's tiled_sample); tiles fp32 [n][C][T][T]; one float4 per thread.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) tile_copy_kernel(float* canvas, float* tiles, srgd_tile_coords tc, int C, int H,
+                                                        int W, int T) {
+  const int t4 = T / 4;
+  const int64_t total = (int64_t)tc.n * C * T * t4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x4 = (int)(i % t4);
+    const int y = (int)((i / t4) % T);
+    const int c = (int)((i / ((int64_t)t4 * T)) % C);
+    const int k = (int)(i / ((int64_t)t4 * T * C));
+    float* cp = canvas + ((int64_t)c * H + tc.yx[k][0] + y) * W + tc.yx[k][1] + x4 * 4;
+    float* tp = tiles + i * 4;
+    if (SCATTER) st_stream_f4(cp, ld_stream_f4(tp));
+    else st_stream_f4(tp, ld_stream_f4(cp));
+  }
+}
+
+// img[c][y][x] = sigma * noise[c][y][x] outside the rectangle [y0,y1) x [x0,x1), unchanged inside (model.py:3392-3396:
+// q_sample of zeros at the next noise level everywhere except the hull of the shifted tile grid)
+__global__ void __launch_bounds__(256) renoise_outside_kernel(float* img, const float* __restrict__ noise, int64_t n,
+                                                              int H, int W, int y0, int y1, int x0, int x1,
+                                                              float sigma) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    if (y < y0 || y >= y1 || x < x0 || x >= x1) img[i] = noise[i] * sigma;
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   int64_t want = (work_items + threads - 1) / threads;
   int64_t cap = (int64_t)sm_count() * ctas_per_sm;
@@ -151,6 +182,51 @@ extern "C" int srgd_finalize_image(const float* img, float* out, int64_t n, srgd
   ProfScope prof(SRGD_PK_OTHER, 0.0, 8.0 * (double)n, as_stream(stream));
   finalize_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(img, out, n);
   SRGD_LAUNCH_OK("finalize_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+static int tile_copy(bool scatter, float* canvas, float* tiles, const srgd_tile_coords* tc, int32_t C, int32_t H,
+                     int32_t W, int32_t T, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(canvas && tiles && tc, "tile gather/scatter: null argument");
+  SRGD_REQUIRE(tc->n >= 1 && tc->n <= SRGD_MAX_TILES_PER_CALL, "tile gather/scatter: n=%d out of range", tc->n);
+  SRGD_REQUIRE(C > 0 && T > 0 && T % 4 == 0 && W % 4 == 0 && H >= T && W >= T, "tile gather/scatter: bad geometry");
+  SRGD_REQUIRE(((uintptr_t)canvas | (uintptr_t)tiles) % 16 == 0, "tile gather/scatter: pointers must be 16-byte aligned");
+  for (int k = 0; k < tc->n; ++k)
+    SRGD_REQUIRE(tc->yx[k][0] >= 0 && tc->yx[k][0] + T <= H && tc->yx[k][1] >= 0 && tc->yx[k][1] + T <= W &&
+                     tc->yx[k][1] % 4 == 0,
+                 "tile gather/scatter: tile %d at (%d,%d) outside the %dx%d canvas or x not a multiple of 4", k,
+                 tc->yx[k][0], tc->yx[k][1], H, W);
+  const int64_t total = (int64_t)tc->n * C * T * (T / 4);
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 32.0 * (double)total, as_stream(stream));
+  if (scatter) tile_copy_kernel<true><<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(canvas, tiles, *tc, C, H, W, T);
+  else tile_copy_kernel<false><<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(canvas, tiles, *tc, C, H, W, T);
+  SRGD_LAUNCH_OK("tile_copy_kernel");
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_gather_tiles(const float* canvas, float* tiles, const srgd_tile_coords* tc, int32_t C, int32_t H,
+                                 int32_t W, int32_t T, srgd_stream_t stream) {
+  return tile_copy(false, const_cast<float*>(canvas), tiles, tc, C, H, W, T, stream);
+}
+
+extern "C" int srgd_scatter_tiles(float* canvas, const float* tiles, const srgd_tile_coords* tc, int32_t C, int32_t H,
+                                  int32_t W, int32_t T, srgd_stream_t stream) {
+  return tile_copy(true, canvas, const_cast<float*>(tiles), tc, C, H, W, T, stream);
+}
+
+extern "C" int srgd_renoise_outside(float* img, const float* noise, int32_t C, int32_t H, int32_t W, int32_t y0,
+                                    int32_t y1, int32_t x0, int32_t x1, float sigma, srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(img && noise && C > 0 && H > 0 && W > 0, "renoise_outside: bad arguments");
+  const int64_t n = (int64_t)C * H * W;
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 8.0 * (double)n, as_stream(stream));
+  renoise_outside_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(img, noise, n, H, W, y0, y1, x0, x1, sigma);
+  SRGD_LAUNCH_OK("renoise_outside_kernel");
   count_launch();
   return SRGD_OK;
 }

@@ -272,7 +272,10 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
     def tiled_sample(self, batch_size=4, tile_size=256, tile_stride=256, condition_x=None, class_label=None,
                      cond_scale=1.0, guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
                      generation_start_steps=0, num_sample_steps=None, with_images=False, with_x0_images=False,
-                     start_white_noise=True, amp=False):
+                     start_white_noise=True, amp=False, shard_tiles=False):
+        """`shard_tiles=True` (extension): with an initialised torch.distributed group the tiles of every step are
+        split over the ranks and exchanged once per step; every rank returns the same image, bit-identical to the
+        single-GPU result (srgd_b200/tiled.py)."""
         num_sample_steps = self.num_sample_steps if num_sample_steps is None else num_sample_steps
         _lib.require_cuda(condition_x, "tiled_sample")
         condition_x = condition_x * 2 - 1
@@ -294,32 +297,26 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
         it, ib, il, ir = plan.inner
         cond_canvas = torch.zeros_like(condition_x)
         cond_canvas[:, :, it:ib, il:ir] = condition_x[:, :, it:ib, il:ir]
-        x_start = img.clone()
-        for i in self._iter(num_sample_steps):
-            if i < generation_start_steps:
-                continue
-            cs = 1.0 if i < guidance_start_steps else cond_scale
-            ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
-            tiles = plan.grids[i % 2]
-            for first in range(0, len(tiles), batch_size):
-                chunk = tiles[first:first + batch_size]
-                xt = torch.cat([img[:, :, a:a + tile_size, b:b + tile_size] for a, b in chunk], 0)
-                ct = torch.cat([cond_canvas[:, :, a:a + tile_size, b:b + tile_size] for a, b in chunk], 0)
-                out, x0 = self.p_sample(xt, steps[i], ct, class_label, cs, ccs, steps[i + 1])
-                for k, (a, b) in enumerate(chunk):
-                    img[:, :, a:a + tile_size, b:b + tile_size] = out[k]
-                    x_start[:, :, a:a + tile_size, b:b + tile_size] = x0[k]
-            if i % 2 == 1:
-                # outside the inner hull the state is replaced by fresh noise at the next noise level
-                # (q_sample of zeros, model.py:3392-3396); the draw covers the whole canvas like the
-                # reference so the RNG stream stays aligned
-                fresh = self._pure_noise_at(torch.randn_like(cond_canvas), steps[i + 1])
-                fresh[:, :, it:ib, il:ir] = img[:, :, it:ib, il:ir]
-                img = fresh
+        x_start = img.clone() if with_x0_images else None
+        bar = self._iter(num_sample_steps)
+        bar_it = iter(bar)
+
+        def on_step(i, cur, cur_x0):
+            next(bar_it, None)                                                  # progress bar tick
             if with_images:
-                images.append(img.clone().cpu())
+                images.append(cur[:, :, top:bottom, left:right].clone().cpu())
             if with_x0_images:
-                x0_images.append(x_start.clone().cpu())
+                x0_images.append(cur_x0[:, :, top:bottom, left:right].clone().cpu())
+
+        from .tiled import CudaTiledOps, run_tiled
+        img = img.contiguous()
+        cond_canvas = cond_canvas.contiguous()
+        img, x_start = run_tiled(CudaTiledOps(self), img, cond_canvas, plan, steps, num_sample_steps, batch_size,
+                                 class_label, cond_scale, guidance_start_steps, class_cond_scale,
+                                 class_guidance_start_steps, generation_start_steps, x_start=x_start, on_step=on_step,
+                                 shard=shard_tiles)
+        for _ in bar_it:
+            pass
         img = self._finalize(img[:, :, top:bottom, left:right].contiguous())
         if with_images:
             return (img, images, x0_images) if with_x0_images else (img, images)

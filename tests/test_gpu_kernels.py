@@ -77,6 +77,36 @@ def test_q_sample_and_finalize(lib):
     torch.testing.assert_close(out.cpu(), ((x0 * 2).clamp(-1, 1) + 1) * 0.5, rtol=0, atol=0)
 
 
+def test_tile_gather_scatter_renoise(lib):
+    """Batched tile orchestration kernels of tiled_sample (model.py:3364-3380, 3392-3396)."""
+    g = torch.Generator().manual_seed(3)
+    H, W, T = 96, 160, 32
+    canvas = torch.randn(1, 3, H, W, generator=g).cuda()
+    coords = [(0, 0), (32, 64), (64, 128), (16, 4), (64, 0)]
+    tc = _lib.TileCoords()
+    tc.n = len(coords)
+    for k, (y, x) in enumerate(coords):
+        tc.yx[k][0], tc.yx[k][1] = y, x
+    tiles = torch.full((len(coords), 3, T, T), float("nan"), device="cuda")
+    _lib.check(lib.srgd_gather_tiles(G.P(canvas), G.P(tiles), C.byref(tc), 3, H, W, T, G.stream()))
+    ref = torch.cat([canvas[:, :, y:y + T, x:x + T] for y, x in coords], 0)
+    assert torch.equal(tiles, ref)
+    dst = torch.zeros_like(canvas)
+    expect = torch.zeros_like(canvas)
+    for k, (y, x) in enumerate(coords):
+        expect[:, :, y:y + T, x:x + T] = tiles[k]
+    _lib.check(lib.srgd_scatter_tiles(G.P(dst), G.P(tiles), C.byref(tc), 3, H, W, T, G.stream()))
+    assert torch.equal(dst, expect)
+    noise = torch.randn(1, 3, H, W, generator=g).cuda()
+    img = canvas.clone()
+    _lib.check(lib.srgd_renoise_outside(G.P(img), G.P(noise), 3, H, W, 16, 80, 32, 128, 0.37, G.stream()))
+    want = noise * 0.37
+    want[:, :, 16:80, 32:128] = canvas[:, :, 16:80, 32:128]
+    assert torch.equal(img, want)
+    tc.yx[0][1] = 130                                                       # tile sticks out of the canvas
+    assert lib.srgd_gather_tiles(G.P(canvas), G.P(tiles), C.byref(tc), 3, H, W, T, G.stream()) == -1
+
+
 # ------------------------------------------------------------------------------------------------
 # convolutions
 # ------------------------------------------------------------------------------------------------
