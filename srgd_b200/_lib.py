@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsrgd_b200.so")
+# SRGD_B200_LIB: developer A/B knob (an alternative build of the same library, srgd_b200/build.py `variant`)
+LIB_PATH = os.environ.get("SRGD_B200_LIB") or os.path.join(HERE, "libsrgd_b200.so")
 
 SRGD_CONV_MAX_SRC = 4
 SRGD_CONV_MAX_PHASE = 20

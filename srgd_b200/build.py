@@ -32,9 +32,12 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), variant: str = "") -> str:
+    """`variant` / `extra_flags` build an A/B copy (libsrgd_b200_<variant>.so, selected with SRGD_B200_LIB) for
+    compile-time experiments; the product library is the default call."""
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
+    lib = LIB if not variant else os.path.join(HERE, f"libsrgd_b200_{variant}.so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "srgd_b200.h"))
@@ -43,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,12 +56,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 // Error plumbing, device check and version for the srgd_b200 C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -54,6 +55,15 @@ int check_device() {
 }
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("SRGD_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached != 0;
+}
 
 // ---- profiling ---------------------------------------------------------------------------------
 bool g_prof_on = false;

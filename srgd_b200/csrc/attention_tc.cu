@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(192, 2) fa_tc_kernel(const __grid_constant__ F
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -272,7 +273,7 @@ extern "C" int srgd_attention_tc(const void* qkv, void* out, int32_t B, int32_t 
   }
   cudaStream_t st = as_stream(stream);
   ProfScope prof(SRGD_PK_FULL_ATTN, 4.0 * (double)B * heads * (double)N * N * 32, 2.0 * (double)B * N * heads * 32 * 4, st);
-  fa_tc_kernel<<<dim3(N / 128, B * heads), 192, FaTcSmem::kTotal, st>>>(kp);
+  SRGD_CUDA_OK(launch_k(fa_tc_kernel, dim3(N / 128, B * heads), dim3(192), FaTcSmem::kTotal, st, kp));
   SRGD_LAUNCH_OK("fa_tc_kernel");
   count_launch();
   return SRGD_OK;

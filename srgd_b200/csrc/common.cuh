@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/srgd_b200.h"
 
@@ -65,6 +66,34 @@ struct ProfScope {
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: kernel N+1 is made resident while the last CTAs of kernel N drain, runs its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) and blocks in pdl_wait() until kernel N has
+// completed and flushed.  ~170 launches per U-Net forward make the launch gap 1-12 % of a step (B = 16 .. 1 tiles).
+// Rule for every kernel launched through launch_k(): ALL threads call pdl_wait() before the first access to
+// global memory that another kernel may have written, and before the first global write.  No kernel issues
+// griddepcontrol.launch_dependents: an early trigger (dependents resident and parked for the whole primary) was
+// measured SLOWER than stream order at B >= 8 and the implicit trigger at CTA exit faster at every batch
+// (profiles/r01_pdl_ab.txt).  SRGD_PDL=0 in the environment restores plain stream serialisation.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 

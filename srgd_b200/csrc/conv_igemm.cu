@@ -111,6 +111,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
   const int tn_log2 = 7 - p.tw_log2 - p.th_log2;
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
   const int tn_log2 = 7 - p.tw_log2 - p.th_log2;
@@ -750,8 +752,7 @@ static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
     configured = true;
   }
   int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
-  conv_igemm_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, st>>>(kp);
-  SRGD_LAUNCH_OK("conv_igemm_kernel");
+  SRGD_CUDA_OK(launch_k(conv_igemm_kernel<BN, STAGES>, dim3(grid), dim3(kThreads), L::kTotal, st, kp));
   count_launch();
   return SRGD_OK;
 }
@@ -765,8 +766,7 @@ static int launch_igemm_t(const ConvKernelParams& kp, cudaStream_t st) {
     configured = true;
   }
   int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
-  conv_igemm_t_kernel<HALO><<<grid, kThreads, L::kTotal, st>>>(kp);
-  SRGD_LAUNCH_OK("conv_igemm_t_kernel");
+  SRGD_CUDA_OK(launch_k(conv_igemm_t_kernel<HALO>, dim3(grid), dim3(kThreads), L::kTotal, st, kp));
   count_launch();
   return SRGD_OK;
 }

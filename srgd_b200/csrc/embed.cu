@@ -13,6 +13,7 @@ namespace srgd {
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, const float* __restrict__ cond,
                                                          int n_cond_rows, int Bx, bf16* __restrict__ out, int B, int H,
                                                          int W) {
+  pdl_wait();
   const int64_t total = (int64_t)B * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int xx = (int)(i % W);
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict_
                                                          const float* __restrict__ bias, float* __restrict__ eps,
                                                          int B, int HW, int C) {
   extern __shared__ float sw[];                          // [COUT][C]
+  pdl_wait();
   for (int i = threadIdx.x; i < COUT * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict_
 
 __global__ void fourier_features_kernel(const float* __restrict__ log_snr, const float* __restrict__ wts,
                                         float* __restrict__ out, int B, int half) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int width = 2 * half + 1;
   if (i >= B * width) return;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const float* __restrict
                                                          const float* __restrict__ bias, float* __restrict__ y, int M,
                                                          int N, int K, int act, int accumulate) {
   extern __shared__ float sx[];                          // [kDrRows][K]
+  pdl_wait();
   const int m0 = blockIdx.y * kDrRows;
   const int rows = min(kDrRows, M - m0);
   for (int i = threadIdx.x; i < rows * K; i += blockDim.x) sx[i] = act_in(x[(int64_t)m0 * K + i], act);
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const float* __restrict
 
 __global__ void add_class_rows_kernel(float* __restrict__ t, const float* __restrict__ table,
                                       const int32_t* __restrict__ labels, int B, int dim, int num_classes) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
   const int b = i / dim, j = i % dim;
@@ -175,9 +180,8 @@ extern "C" int srgd_pack_input(const float* x, const float* cond, int32_t n_cond
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   ProfScope prof(SRGD_PK_OTHER, 0.0, (double)B * H * W * (6 * 4 + 128), as_stream(stream));
-  pack_input_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, cond, n_cond_rows, Bx,
-                                                               reinterpret_cast<bf16*>(out), B, H, W);
-  SRGD_LAUNCH_OK("pack_input_kernel");
+  SRGD_CUDA_OK(launch_k(pack_input_kernel, dim3((int)blocks), dim3(256), 0, as_stream(stream), x, cond, n_cond_rows, Bx,
+                        reinterpret_cast<bf16*>(out), B, H, W));
   count_launch();
   return SRGD_OK;
 }
@@ -194,9 +198,8 @@ extern "C" int srgd_final_conv(const void* h, const float* w, const float* bias,
   int64_t blocks = (n_groups + 7) / 8;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   ProfScope prof(SRGD_PK_OTHER, 0.0, (double)B * H * W * (C * 2.0 + 12.0), as_stream(stream));
-  final_conv_kernel<3><<<(int)blocks, 256, (size_t)3 * C * sizeof(float), as_stream(stream)>>>(
-      reinterpret_cast<const bf16*>(h), w, bias, eps, B, H * W, C);
-  SRGD_LAUNCH_OK("final_conv_kernel");
+  SRGD_CUDA_OK(launch_k(final_conv_kernel<3>, dim3((int)blocks), dim3(256), (size_t)3 * C * sizeof(float),
+                        as_stream(stream), reinterpret_cast<const bf16*>(h), w, bias, eps, B, H * W, C));
   count_launch();
   return SRGD_OK;
 }
@@ -208,8 +211,8 @@ extern "C" int srgd_fourier_features(const float* log_snr, const float* weights,
   SRGD_REQUIRE(log_snr && weights && out && B > 0 && half_dim > 0, "fourier_features: bad arguments");
   const int total = B * (2 * half_dim + 1);
   ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
-  fourier_features_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(log_snr, weights, out, B, half_dim);
-  SRGD_LAUNCH_OK("fourier_features_kernel");
+  SRGD_CUDA_OK(launch_k(fourier_features_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), log_snr,
+                        weights, out, B, half_dim));
   count_launch();
   return SRGD_OK;
 }
@@ -222,9 +225,8 @@ extern "C" int srgd_dense_rows(const float* x, const float* w, const float* bias
   SRGD_REQUIRE((M + kDrRows - 1) / kDrRows <= 65535, "dense_rows: too many rows");
   dim3 grid((N + 7) / 8, (M + kDrRows - 1) / kDrRows);
   ProfScope prof(SRGD_PK_OTHER, 0.0, 4.0 * ((double)N * K + (double)M * (N + K)), as_stream(stream));
-  dense_rows_kernel<<<grid, 256, (size_t)kDrRows * K * sizeof(float), as_stream(stream)>>>(x, w, bias, y, M, N, K,
-                                                                                           act_in, accumulate);
-  SRGD_LAUNCH_OK("dense_rows_kernel");
+  SRGD_CUDA_OK(launch_k(dense_rows_kernel, grid, dim3(256), (size_t)kDrRows * K * sizeof(float), as_stream(stream), x, w,
+                        bias, y, M, N, K, act_in, accumulate));
   count_launch();
   return SRGD_OK;
 }
@@ -236,8 +238,8 @@ extern "C" int srgd_add_class_rows(float* t, const float* table, const int32_t* 
   SRGD_REQUIRE(t && table && labels_dev && B > 0 && dim > 0, "add_class_rows: bad arguments");
   const int total = B * dim;
   ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
-  add_class_rows_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(t, table, labels_dev, B, dim, num_classes);
-  SRGD_LAUNCH_OK("add_class_rows_kernel");
+  SRGD_CUDA_OK(launch_k(add_class_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, as_stream(stream), t, table,
+                        labels_dev, B, dim, num_classes));
   count_launch();
   return SRGD_OK;
 }

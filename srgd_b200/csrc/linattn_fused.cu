@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restric
   float* red = reinterpret_cast<float*>(merge_smem + (size_t)C * 64);
   for (int i = threadIdx.x; i < C * 4; i += 128)           // 4 x 16 B per output channel
     wsm[i] = __ldg(reinterpret_cast<const uint4*>(wout + (int64_t)(i >> 2) * kLfHid + h * 32) + (i & 3));
+  pdl_wait();                                             // weights above are never written by a kernel
   // each warp (cq) folds every fourth split record; the four partial results are combined through shared memory
   const float* base = part + (int64_t)b * splits * (34 * kLfHid) + h * 32 + d;
   const int64_t sstride = 34 * kLfHid;
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -592,7 +595,7 @@ static int launch_la_out(const LaOutParams& kp, int chunks, int B, cudaStream_t 
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  la_out_kernel<C><<<dim3(chunks, B), 320, L::kTotal, st>>>(kp);
+  SRGD_CUDA_OK(launch_k(la_out_kernel<C>, dim3(chunks, B), dim3(320), L::kTotal, st, kp));
   SRGD_LAUNCH_OK("la_out_kernel");
   count_launch();
   return SRGD_OK;
@@ -665,9 +668,10 @@ extern "C" int srgd_linear_attention_block(const void* x, const float* inv_norm,
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaCtxSmem::kTotal));
     configured = true;
   }
-  la_ctx_kernel<<<dim3(splits, B), 320, LaCtxSmem::kTotal, st>>>(ap);
+  SRGD_CUDA_OK(launch_k(la_ctx_kernel, dim3(splits, B), dim3(320), LaCtxSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_kernel");
-  la_merge_mb_kernel<<<B * 4, 128, (size_t)C * 64 + 4 * 34 * 32 * 4, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, splits, C);
+  SRGD_CUDA_OK(launch_k(la_merge_mb_kernel, dim3(B * 4), dim3(128), (size_t)C * 64 + 4 * 34 * 32 * 4, st, part,
+                        reinterpret_cast<const bf16*>(out_w), bd, splits, C));
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
   count_launch(2);
 

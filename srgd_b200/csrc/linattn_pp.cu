@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(576, 1) la_ctx_pp_kernel(const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
   const int nsub = 2 * ntiles;
 
   if (warp == 0 && lane == 0) {
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -639,9 +641,10 @@ int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, cons
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_out_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaOutPpSmem::kTotal));
     configured = true;
   }
-  la_ctx_pp_kernel<<<dim3(splits, B), 576, LaCtxPpSmem::kTotal, st>>>(ap);
+  SRGD_CUDA_OK(launch_k(la_ctx_pp_kernel, dim3(splits, B), dim3(576), LaCtxPpSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_pp_kernel");
-  la_merge_mb_kernel<<<B * 4, 128, 128 * 64 + 4 * 34 * 32 * 4, st>>>(part, reinterpret_cast<const bf16*>(out_w), bd, 2 * splits, 128);
+  SRGD_CUDA_OK(launch_k(la_merge_mb_kernel, dim3(B * 4), dim3(128), (size_t)(128 * 64 + 4 * 34 * 32 * 4), st, part,
+                        reinterpret_cast<const bf16*>(out_w), bd, 2 * splits, 128));
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
 
   LaOutPpParams bp;
@@ -655,7 +658,7 @@ int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, cons
   bp.x = reinterpret_cast<const bf16*>(x);
   bp.out = reinterpret_cast<bf16*>(out);
   bp.chunks = splits; bp.tiles_per_sample = tiles;
-  la_out_pp_kernel<<<dim3(splits, B), 576, LaOutPpSmem::kTotal, st>>>(bp);
+  SRGD_CUDA_OK(launch_k(la_out_pp_kernel, dim3(splits, B), dim3(576), LaOutPpSmem::kTotal, st, bp));
   SRGD_LAUNCH_OK("la_out_pp_kernel");
   count_launch(3);
   return SRGD_OK;

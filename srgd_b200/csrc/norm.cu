@@ -6,6 +6,8 @@
 // math, per-(sample, channel) affine folded into one FMA:  y = silu(x * A[c] + B[c]) with
 //   A = rstd*gamma*(scale+1),  B = (beta - mean*rstd*gamma)*(scale+1) + shift.
 // Algorithmic bytes: 2 B read + 2 B written per element (+2 B when a residual is added).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tiles.h"
 
@@ -22,6 +24,7 @@ constexpr int kGroups = 8;
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials,
                                                           float* __restrict__ stats, int H, int W, int C,
                                                           TileGeom g) {
+  pdl_wait();
   const int n = blockIdx.x;
   const int tb = n >> g.tn_log2, n_i = n & ((1 << g.tn_log2) - 1);
   const int tiles_per_b = g.tiles_x * g.tiles_y;
@@ -118,12 +121,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
                                                        const bf16* residual, bf16* y, float* __restrict__ inv_out,
                                                        const float* __restrict__ fin_w, const float* __restrict__ fin_b,
-                                                       float* __restrict__ eps, int HW, int C) {
+                                                       float* __restrict__ eps, int HW, int C, int reverse) {
   extern __shared__ float sm[];                          // !REG: A[C] | B[C] | (FINAL: fin_w[3][C])
+  pdl_wait();                                            // stats come from the preceding gn_finalize launch
   float* sA = sm;
   float* sB = sm + C;
   float* sW = sm + 2 * C;
-  const int b = blockIdx.y;
+  // reverse: walk the tensor from its end.  The producer conv wrote x front to back, so its tail is what the
+  // 126 MB L2 still holds; reading it first turns ~1/3 of a 268 MB pass into L2 hits, and leaves the head of y
+  // in L2 for the consumer conv, which starts at the front again.
+  const int b = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int bs = b % Bx;
   const int G = C / kGroups;
   const int vec_per_pix = C / 8;
@@ -141,7 +148,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
     }
   };
   if (REG) {
-    const int c0 = (int)(threadIdx.x % vec_per_pix) * 8;
+    const int cv = (int)(threadIdx.x % vec_per_pix);
+    const int c0 = (reverse ? vec_per_pix - 1 - cv : cv) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) coef(c0 + j, ra[j], rb[j]);
     if (FINAL) {
@@ -167,17 +175,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
     const int64_t i1 = i + stride;
     const bool has1 = i1 < total;
+    const int64_t j0 = reverse ? total - 1 - i : i, j1 = reverse ? total - 1 - i1 : i1;
     uint4 xv[2], rv[2];
-    xv[0] = ld_stream(xs + i * 8);
-    if (has1) xv[1] = ld_stream(xs + i1 * 8);
+    xv[0] = ld_stream(xs + j0 * 8);
+    if (has1) xv[1] = ld_stream(xs + j1 * 8);
     if (HAS_RES) {
-      rv[0] = ld_stream(rs + i * 8);
-      if (has1) rv[1] = ld_stream(rs + i1 * 8);
+      rv[0] = ld_stream(rs + j0 * 8);
+      if (has1) rv[1] = ld_stream(rs + j1 * 8);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !has1) break;
-      const int64_t iu = u ? i1 : i;
+      const int64_t iu = u ? j1 : j0;
       const int c0 = (int)(iu % vec_per_pix) * 8;
       float f[8];
       unpack8(xv[u], f);
@@ -248,6 +257,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int LP>
 __global__ void __launch_bounds__(256) pixel_inv_norm_kernel(const bf16* __restrict__ x, float* __restrict__ inv,
                                                              int64_t M, int C) {
+  pdl_wait();
   const int vec_per_pix = C / 8;
   const int sub = threadIdx.x % LP;
   const int64_t pix_per_block = blockDim.x / LP;
@@ -269,6 +279,7 @@ template <int LP, bool HAS_RES>
 __global__ void __launch_bounds__(256) rmsnorm_residual_kernel(const bf16* x, const float* __restrict__ g,
                                                                const bf16* residual, bf16* y, int64_t M, int C,
                                                                float sqrt_c) {
+  pdl_wait();
   const int vec_per_pix = C / 8;
   const int sub = threadIdx.x % LP;
   const int64_t pix_per_block = blockDim.x / LP;
@@ -307,6 +318,15 @@ __global__ void __launch_bounds__(256) rmsnorm_residual_kernel(const bf16* x, co
   }
 }
 
+static int gn_reverse() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("SRGD_GN_REVERSE");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached;
+}
+
 static int stream_grid(int64_t items_per_block_total, int ctas_per_sm) {
   int64_t cap = (int64_t)sm_count() * ctas_per_sm;
   if (items_per_block_total < 1) items_per_block_total = 1;
@@ -326,8 +346,7 @@ extern "C" int srgd_groupnorm_finalize(const float* gn_partials, float* stats, i
   const TileGeom g = tile_geom(B, H, W);
   SRGD_REQUIRE(g.tn_log2 <= 2, "groupnorm_finalize: needs H*W >= 32");
   ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)g.m_tiles * 8 * 8 * 2 * 4, as_stream(stream));
-  gn_finalize_kernel<<<B, 1024, 0, as_stream(stream)>>>(gn_partials, stats, H, W, C, g);
-  SRGD_LAUNCH_OK("gn_finalize_kernel");
+  SRGD_CUDA_OK(launch_k(gn_finalize_kernel, dim3(B), dim3(1024), 0, as_stream(stream), gn_partials, stats, H, W, C, g));
   count_launch();
   return SRGD_OK;
 }
@@ -369,9 +388,9 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   const int vpp = C / 8;
   const bool reg = (vpp & (vpp - 1)) == 0 && vpp <= 256;
 #define SRGD_GN_LAUNCH(RES, INV, R)                                                                              \
-  gn_apply_kernel<RES, INV, false, R><<<grid, 256, R ? 0 : smem, cst>>>(xr, Bx, stats, gamma, beta, scale_shift,  \
-                                                                       ss_stride, rr, yr, inv_out, nullptr,      \
-                                                                       nullptr, nullptr, H * W, C)
+  SRGD_CUDA_OK(launch_k(gn_apply_kernel<RES, INV, false, R>, grid, dim3(256), R ? 0 : smem, cst, xr, Bx, stats,   \
+                        gamma, beta, scale_shift, ss_stride, rr, yr, inv_out, nullptr, nullptr, nullptr, H * W, C, \
+                        gn_reverse()))
   if (inv_out != nullptr && C == 128) SRGD_GN_LAUNCH(true, 16, true);
   else if (inv_out != nullptr) SRGD_GN_LAUNCH(true, 32, true);
   else if (residual && reg) SRGD_GN_LAUNCH(true, 0, true);
@@ -379,7 +398,6 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   else if (reg) SRGD_GN_LAUNCH(false, 0, true);
   else SRGD_GN_LAUNCH(false, 0, false);
 #undef SRGD_GN_LAUNCH
-  SRGD_LAUNCH_OK("gn_apply_kernel");
   count_launch();
   return SRGD_OK;
 }
@@ -400,10 +418,10 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
   const size_t smem = (size_t)C * 5 * sizeof(float);
   ProfScope prof(SRGD_PK_GN_APPLY, 2.0 * B * H * W * C * 3, (double)B * H * W * (C * 4.0 + 12.0), as_stream(stream));
   (void)smem;
-  gn_apply_kernel<true, 0, true, true><<<grid, 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0, reinterpret_cast<const bf16*>(residual), nullptr,
-      nullptr, final_w, final_b, eps, H * W, C);
-  SRGD_LAUNCH_OK("gn_apply_kernel(final)");
+  SRGD_CUDA_OK(launch_k(gn_apply_kernel<true, 0, true, true>, grid, dim3(256), 0, as_stream(stream),
+                        reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0,
+                        reinterpret_cast<const bf16*>(residual), nullptr, nullptr, final_w, final_b, eps, H * W, C,
+                        gn_reverse()));
   count_launch();
   return SRGD_OK;
 }
@@ -416,13 +434,13 @@ extern "C" int srgd_pixel_inv_norm(const void* x, float* inv, int64_t M, int32_t
   ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)M * C * 2.0 + (double)M * 4.0, as_stream(stream));
   if (C / 8 >= 32) {
     const int grid = stream_grid((M + 7) / 8, 8);
-    pixel_inv_norm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+    SRGD_CUDA_OK(launch_k(pixel_inv_norm_kernel<32>, dim3(grid), dim3(256), 0, as_stream(stream), xr, inv, M, C));
   } else if (C / 8 == 16) {
     const int grid = stream_grid((M + 15) / 16, 8);
-    pixel_inv_norm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+    SRGD_CUDA_OK(launch_k(pixel_inv_norm_kernel<16>, dim3(grid), dim3(256), 0, as_stream(stream), xr, inv, M, C));
   } else {
     const int grid = stream_grid((M + 31) / 32, 8);
-    pixel_inv_norm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(xr, inv, M, C);
+    SRGD_CUDA_OK(launch_k(pixel_inv_norm_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), xr, inv, M, C));
   }
   SRGD_LAUNCH_OK("pixel_inv_norm_kernel");
   count_launch();
@@ -443,8 +461,10 @@ extern "C" int srgd_rmsnorm_residual(const void* x, const float* g, const void* 
 #define SRGD_RMS(LP)                                                                                     \
   do {                                                                                                   \
     const int grid = stream_grid((M + (256 / LP) - 1) / (256 / LP), 8);                                  \
-    if (residual) rmsnorm_residual_kernel<LP, true><<<grid, 256, 0, st>>>(xr, g, rr, yr, M, C, sc);      \
-    else rmsnorm_residual_kernel<LP, false><<<grid, 256, 0, st>>>(xr, g, rr, yr, M, C, sc);              \
+    if (residual)                                                                                        \
+      SRGD_CUDA_OK(launch_k(rmsnorm_residual_kernel<LP, true>, dim3(grid), dim3(256), 0, st, xr, g, rr, yr, M, C, sc)); \
+    else                                                                                                 \
+      SRGD_CUDA_OK(launch_k(rmsnorm_residual_kernel<LP, false>, dim3(grid), dim3(256), 0, st, xr, g, rr, yr, M, C, sc)); \
   } while (0)
   if (C / 8 >= 32) SRGD_RMS(32);
   else if (C / 8 == 16) SRGD_RMS(16);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(
     const float* __restrict__ x, const float* __restrict__ ec, const float* __restrict__ en,
     const float* __restrict__ noise, float* img, float* __restrict__ x0out, int64_t n4, int64_t n,
     srgd_step_scalars s) {
+  pdl_wait();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 xv = ld_stream_f4(x + 4 * i);
@@ -142,10 +143,11 @@ extern "C" int srgd_sampler_step(const float* x, const float* eps_cond, const fl
   const int key = (eps_null ? 4 : 0) | (noise ? 2 : 0) | (x_start ? 1 : 0);
   ProfScope prof(SRGD_PK_SAMPLER, 0.0,
                  4.0 * (double)n * (3 + (eps_null ? 1 : 0) + (noise ? 1 : 0) + (x_start ? 1 : 0)), st);
+  cudaError_t launch_err = cudaSuccess;
 #define SRGD_CASE(K, A, B_, C)                                                                    \
   case K:                                                                                         \
-    sampler_step_kernel<A, B_, C><<<grid, 256, 0, st>>>(x, eps_cond, eps_null, noise, img_next,   \
-                                                        x_start, n4, n, *s);                      \
+    launch_err = launch_k(sampler_step_kernel<A, B_, C>, dim3(grid), dim3(256), 0, st, x, eps_cond, \
+                          eps_null, noise, img_next, x_start, n4, n, *s);                         \
     break;
   switch (key) {
     SRGD_CASE(0, false, false, false)
@@ -158,7 +160,7 @@ extern "C" int srgd_sampler_step(const float* x, const float* eps_cond, const fl
     SRGD_CASE(7, true, true, true)
   }
 #undef SRGD_CASE
-  SRGD_LAUNCH_OK("sampler_step_kernel");
+  SRGD_CUDA_OK(launch_err);
   count_launch();
   return SRGD_OK;
 }
