@@ -277,20 +277,19 @@ def main():
     # FLOPs actually executed by the conv launches (2*M*N*K credited per launch by the library); the 1x1 convs of
     # the fused LinearAttention blocks are not in this kernel any more
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
-    # DRAM traffic of the same kernel from the committed ncu capture of this workload (profiles/): bytes per launch
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture of this workload (profiles/):
+    # dram__bytes_read.sum + dram__bytes_write.sum averaged over the conv launches of one step
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_launches_latest.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_full_conv_latest.json")
     if os.path.exists(tpath) and args.batch == 16 and ccs == 1.0:
         try:
-            kk = json.load(open(tpath))["kernels"]
-            by = sum(v["dram_bytes"] for k, v in kk.items() if k.startswith("conv_igemm"))
-            n = sum(v["launches"] for k, v in kk.items() if k.startswith("conv_igemm"))
-            traffic = by / max(n, 1)
+            kk = json.load(open(tpath))
+            traffic = sum(o["dram_bytes"] for o in kk) / max(len(kk), 1)
         except Exception:
             traffic = None
     roof = dict(bound="tensor", kernel="conv_igemm_kernel (tcgen05 implicit GEMM, all conv3x3/1x1/7x7 launches of a step)",
                 achieved=conv_tflops, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=conv_tflops / pk["bf16_tflops"],
-                traffic=traffic, traffic_unit="DRAM bytes per conv launch (ncu dram__bytes_read+write, profiles/ncu_launches_latest.json)",
+                traffic=traffic, traffic_unit="DRAM bytes per conv launch (ncu dram__bytes_read+write, profiles/ncu_full_conv_latest.json)",
                 achieved_per_launch_flops=conv["flops"] / max(conv["launches"], 1), peak_source=pk["source"],
                 algorithmic=f"{conv['flops'] / 1e9 / nfe_per_step:.2f} GFLOP per tile-NFE (2*M*N*K of every conv launch) "
                             f"x {nfe_per_step} tile-NFE per step",

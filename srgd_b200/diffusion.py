@@ -81,6 +81,10 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
         self.loss_type = loss_type
         self.progress = True
         self.last_step_launches = 0
+        # None: noise is drawn by the generator of the state's device (what the reference does on a GPU).
+        # "cpu": every draw comes from torch's global CPU generator and is copied over -- same shapes, same order,
+        # so a run reproduces the noise stream of the reference run on the CPU with the same seed (parity tests).
+        self.rng_device = None
 
     @property
     def device(self):
@@ -88,6 +92,11 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
 
     def set_seed(self, seed):
         torch.cuda.manual_seed(seed)
+
+    def _randn(self, shape, device):
+        if self.rng_device is not None and torch.device(self.rng_device).type == "cpu":
+            return torch.randn(tuple(shape)).to(device, non_blocking=False)
+        return torch.randn(tuple(shape), device=device)
 
     # ---------------------------------------------------------------------------------------
     # per-step scalars (model.py:3127-3134, 3168) -- same fp32 tensor ops, evaluated on the host
@@ -169,7 +178,7 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
         if float(_host_scalar(time_next)) == 0.0:                              # model.py:3184
             return self._update(x, eps_c, eps_n, None, s)
         if noise is None:
-            noise = torch.randn_like(x)                                         # model.py:3187
+            noise = self._randn(x.shape, x.device)                              # model.py:3187
         return self._update(x, eps_c, eps_n, noise.contiguous().float(), s)
 
     # ---------------------------------------------------------------------------------------
@@ -177,7 +186,7 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
     # ---------------------------------------------------------------------------------------
     def q_sample(self, x_start, times, noise=None, return_alpha_sigma_sum=False):
         if noise is None:
-            noise = torch.randn_like(x_start)
+            noise = self._randn(x_start.shape, x_start.device)
         times_t = times if torch.is_tensor(times) else torch.tensor(times)
         log_snr = self.log_snr(times_t.float())
         if x_start.is_cuda and log_snr.numel() == 1:
@@ -237,7 +246,7 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
             start = 1. - generation_start_steps / num_sample_steps
             img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32))
         else:
-            img = torch.randn(shape, device=dev)                                # RNG draw #0 (model.py:3203)
+            img = self._randn(shape, dev)                                       # RNG draw #0 (model.py:3203)
         images = [img.clone().cpu()] if with_images else None
         x0_images = [img.clone().cpu()] if with_x0_images else None
         steps = torch.linspace(1., 0., num_sample_steps + 1)                    # host copy of model.py:3213
@@ -286,7 +295,7 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
             start = 1. - generation_start_steps / num_sample_steps
             img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32))
         elif start_white_noise:
-            img = torch.randn(condition_x.shape, device=self.device)            # RNG draw #0 (model.py:3311)
+            img = self._randn(condition_x.shape, self.device)                   # RNG draw #0 (model.py:3311)
         else:
             img, _ = self.q_sample(condition_x, torch.tensor(1., dtype=torch.float32))
         top, bottom, left, right = plan.crop

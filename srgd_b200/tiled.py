@@ -36,7 +36,7 @@ class CudaTiledOps:
         self.d = diffusion
 
     def randn(self, shape, device):
-        return torch.randn(shape, device=device)
+        return self.d._randn(shape, device)
 
     def p_sample(self, xt, t, ct, label, cs, ccs, t_next, noise):
         return self.d.p_sample(xt, t, ct, label, cs, ccs, t_next, noise=noise)

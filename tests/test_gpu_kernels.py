@@ -130,8 +130,8 @@ CONV_CASES = [
 
 @pytest.fixture(params=["auto", "n", "t"])
 def conv_variant(request):
-    """auto: channels-as-M kernel for 128-wide Cout slabs (halo-reuse variant where it applies); n: force the
-    pixels-as-M kernel; t: channels-as-M without halo reuse."""
+    """auto: channels-as-M kernel for 128-wide Cout slabs and for short-K convs (halo-reuse variant where it
+    applies); n: force the pixels-as-M kernel; t: channels-as-M without halo reuse."""
     import os
     if request.param != "auto":
         os.environ["SRGD_CONV_VARIANT"] = request.param
@@ -158,7 +158,7 @@ def test_conv_matches_torch(lib, conv_variant, B, H, W, cins, Cout, ks, direct):
     assert rel_err(got, ref) < 1e-2, f"rel err {rel_err(got, ref)}"
 
 
-def test_conv_epilogue_variants(lib):
+def test_conv_epilogue_variants(lib, conv_variant):
     g = torch.Generator().manual_seed(5)
     B, H, W, Cin, Cout = 2, 16, 16, 128, 512
     x = G.bf16_round(torch.randn(B, Cin, H, W, generator=g))

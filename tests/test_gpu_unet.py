@@ -197,6 +197,31 @@ def test_tiled_sample_vs_oracle():
     assert p >= 45.0
 
 
+def test_config1_vs_reference_golden():
+    """BASELINE.json configs[0] end to end against the UNMODIFIED reference run on the CPU in fp32
+    (tests/golden/make_golden_config1.py: shipped conf dim 128, 250 steps, one synthetic 64x64 LR image through PIL
+    bicubic x4, label 0, class_cond_scale 1.0, seed 71, inference.py's tiled_sample call).  `rng_device = "cpu"`
+    replays the reference's noise stream (global CPU generator, same shapes in the same order).
+    Bar: final-image PSNR >= 45 dB (north_star)."""
+    from PIL import Image
+    g = load("config1_full")
+    spec = O.UnetSpec()
+    diff = make_diffusion(spec, O.make_state_dict(spec, 1234, init="torch"), 256, int(g["steps"]))
+    diff.rng_device = "cpu"
+    hr = Image.fromarray(g["lr"], mode="RGB").resize((256, 256), resample=Image.BICUBIC)      # inference.py:71-74
+    cond01 = torch.from_numpy(np.array(hr, dtype=np.uint8)).permute(2, 0, 1).float().div(255.)[None]
+    assert torch.equal(cond01, T(g["cond_u8"]).float().div(255.)), "PIL bicubic pre-upscale differs from the fixture"
+    torch.manual_seed(int(g["seed"]))
+    img = diff.tiled_sample(batch_size=int(g["batch_size"]), condition_x=cond01.cuda(),
+                            class_label=torch.tensor([int(g["label"])]).cuda(), class_cond_scale=1.0,
+                            num_sample_steps=int(g["steps"])).cpu()
+    ref = T(g["img"])
+    p = G.psnr(img, ref)
+    print(f"config 1 (reference CPU fp32 vs B200 bf16, {int(g['steps'])} steps): PSNR {p:.2f} dB, "
+          f"max-abs {float((img - ref).abs().max()):.4f}")
+    assert img.shape == ref.shape and p >= 45.0
+
+
 def test_launch_count_reported():
     diff, sd, spec = build("full")
     x = torch.randn(1, 3, 64, 64, device="cuda")

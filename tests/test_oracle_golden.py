@@ -138,3 +138,16 @@ def test_tiled_sample(golden_dir):
                          class_cond_scale=float(g["ccs"]), num_sample_steps=int(g["nsteps"]))
     assert img.shape == (1, 3, 272, 264)
     torch.testing.assert_close(img, T(g["img"]), rtol=0, atol=5e-4)
+
+
+def test_config1_full_size_three_steps(golden_dir):
+    """The oracle at the shipped width and tile size (dim 128, 256x256, label 0, scale 1.0, seed 71) against three
+    steps of the unmodified reference's tiled_sample (tests/golden/make_golden_config1.py with GOLDEN_STEPS=3)."""
+    g = _load(golden_dir, "config1_3")
+    spec = O.UnetSpec()
+    sd = O.make_state_dict(spec, 1234, init="torch")
+    cond01 = T(g["cond_u8"]).float().div(255.)
+    torch.manual_seed(int(g["seed"]))
+    img = O.tiled_sample(sd, spec, int(g["batch_size"]), cond01, torch.tensor([int(g["label"])]),
+                         num_sample_steps=int(g["steps"]))
+    torch.testing.assert_close(img[..., ::2, ::2], T(g["img_sub2"]), rtol=0, atol=5e-4)
