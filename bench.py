@@ -198,6 +198,8 @@ def main():
     img = torch.randn(B, 3, TILE, TILE, device=dev)
     with torch.inference_mode():
         img = run_steps(img, 0, args.warmup)
+        if world > 1:                              # warm-up covers every op of the timed region, the gather included
+            sharding.gather_rows(diff._finalize(img), [B] * world, dst=0)   # (first use sets up NCCL's P2P channels)
         barrier()
         launches_before = 0
         sampler = ClockSampler(local) if rank == 0 else None

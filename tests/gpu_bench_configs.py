@@ -42,17 +42,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:                       # torchrun: the tiled configurations with the tiles of a step split over the ranks
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = O.UnetSpec()
     unet = M.ConditionalSRUnet(dim=128, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
     diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=256, num_sample_steps=250)
     diff.load_state_dict(O.make_state_dict(spec, 1234), strict=True)
-    diff = diff.eval().to("cuda:0")
+    diff = diff.eval().to(torch.device("cuda", local))
     diff.progress = False
     n = a.steps
     with torch.inference_mode():
         # configs[2]: CFG 3.0, batch 32, each test_label
         cond = torch.cat([synth(64, i) for i in range(32)]).cuda()
-        for lab in (0, 1, 2):
+        for lab in ((0, 1, 2) if world == 1 else ()):
             label = torch.tensor([lab], device="cuda")
             diff.sample(batch_size=32, condition_x=cond, class_label=label, class_cond_scale=3.0, num_sample_steps=2)
             # generation_start_steps skips the first 250-n steps: the timed steps are the last n of the real schedule
@@ -65,13 +72,26 @@ def main():
         for name, lr, bs in (("configs[4]", 128, 9), ("configs[3]", 512, 27)):
             c = synth(lr).cuda()
             label = torch.tensor([0], device="cuda")
+            if world > 1:
+                bs = max(1, -(-81 // world) if lr == 512 else -(-9 // world))      # one minibatch per rank per step
+            shard = world > 1
             diff.tiled_sample(batch_size=bs, condition_x=c, class_label=label, num_sample_steps=250,
-                              generation_start_steps=248)
+                              generation_start_steps=248, shard_tiles=shard)
+            if world > 1:
+                dist.barrier()
             ms = timed(lambda: diff.tiled_sample(batch_size=bs, condition_x=c, class_label=label,
-                                                 num_sample_steps=250, generation_start_steps=250 - n))
+                                                 num_sample_steps=250, generation_start_steps=250 - n,
+                                                 shard_tiles=shard))
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
             per = ms / n
-            print(f"{name}: tiled_sample() {lr}x{lr} LR, minibatch {bs}: {per:.2f} ms/step (mean of even+odd grids) -> "
-                  f"{1 / (per * 250e-3):.4f} images/s", flush=True)
+            if rank == 0:
+                print(f"{name}: tiled_sample() {lr}x{lr} LR on {world} GPU(s), minibatch {bs}: {per:.2f} ms/step (mean of "
+                      f"even+odd grids) -> {1 / (per * 250e-3):.4f} images/s", flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
