@@ -130,11 +130,12 @@ typedef struct srgd_conv_desc {
   int32_t act;             /* 0 none, 1 SiLU (applied after bias, before residual)             */
   int32_t out_mode;
   void* out;               /* bf16                                                             */
-  float* gn_partials;      /* NULL, or fp32 [m_tiles*8][8][2]: per (M-tile, pixel quarter, column half) sum
-                              and sum of squares per GroupNorm group of the fp32 result (model.py:247) */
+  float* gn_partials;      /* NULL, or fp32 [m_tiles][S][8][2], S = samples spanned by one 128-pixel M tile
+                              (1 when Ho*Wo >= 128): sum and sum of squares per GroupNorm group of the fp32
+                              result (model.py:247) over the pixels of that (M tile, sample)               */
 } srgd_conv_desc;
 
-/* Number of 128-pixel M tiles the kernel will use for (B,Ho,Wo) -- sizes gn_partials. */
+/* Number of 64-byte gn_partials records the kernel writes for (B,Ho,Wo): m_tiles * S. */
 int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo);
 int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream);
 /* Same contract on CUDA cores, one thread per output element.  Debug/verification path used by
@@ -144,7 +145,8 @@ int srgd_conv_direct(const srgd_conv_desc* d, srgd_stream_t stream);
 /* ------------------------------------------------------------------------------------------
  * GroupNorm(8 groups, eps 1e-5) + (scale+1, shift) + SiLU (+ residual)   model.py:247-258, 285
  * ------------------------------------------------------------------------------------------ */
-/* Reduce the conv epilogue partials to mean / rstd per (sample, group): stats[B][8][2]. */
+/* Reduce the conv epilogue partials to mean / rstd per (sample, group): stats[B][8][2].  The product path does
+ * not launch this: srgd_groupnorm_apply* fold the partials themselves when given gn_partials instead of stats. */
 int srgd_groupnorm_finalize(const float* gn_partials, float* stats, int32_t B, int32_t H, int32_t W,
                             int32_t C, srgd_stream_t stream);
 /* Stand-alone statistics pass over a bf16 NHWC tensor (used when the producer was not a conv). */
@@ -153,18 +155,21 @@ int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int32_t H, int3
 /* y = SiLU( (GN(x)*gamma+beta) * (scale+1) + shift ) [+ residual].  scale_shift: fp32, row b at
  * scale_shift + b*ss_stride holds [scale(C) | shift(C)] (model.py:279), or NULL.  Row b of the
  * output reads sample (b % Bx) of x and stats (CFG halves sharing one conv result).  y may alias
- * x when Bx == B.  inv_out (optional, residual variant with C in {128,256} only): fp32 [B*H*W],
+ * x when Bx == B.  Statistics: exactly one of `stats` ([Bx][8][2] mean, rstd) and `gn_partials` (the records
+ * srgd_conv_igemm wrote for x with the same (Bx,H,W); every block folds its sample's records in fp64 in a
+ * fixed order, which replaces the srgd_groupnorm_finalize launch) is non-NULL.  inv_out (optional, residual variant with C in {128,256} only): fp32 [B*H*W],
  * receives 1 / max(||y[pixel,:]||_2, 1e-12) of the stored bf16 row -- the RMSNorm statistic of the
  * attention block that consumes y (model.py:207), saving srgd_pixel_inv_norm's extra pass. */
-int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
-                         const float* beta, const float* scale_shift, int64_t ss_stride,
+int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gn_partials,
+                         const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                          const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
                          int32_t C, srgd_stream_t stream);
 
 /* Last ResnetBlock of the network fused with the final 1x1 conv (model.py:674-675, 724-725):
  * eps[b][o][y][x] = final_b[o] + sum_c final_w[o][c] * ( SiLU(GN(x)*gamma+beta) + residual )[b][y][x][c],
  * fp32 NCHW out, o < 3; the normalised activation itself is never stored.  C must be 128. */
-int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gamma, const float* beta,
+int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gn_partials,
+                               const float* gamma, const float* beta,
                                const void* residual, const float* final_w, const float* final_b,
                                float* eps, int32_t B, int32_t H, int32_t W, int32_t C,
                                srgd_stream_t stream);

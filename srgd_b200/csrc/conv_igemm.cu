@@ -67,7 +67,7 @@ struct ConvSmem {
   static constexpr int kBarOffset = STAGES * kStageBytes;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr, gn staging
   static constexpr int kGnOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int kGnBytes = 8 * (BN / 8) * 2 * 4;      // one staging row per epilogue warp
+  static constexpr int kGnBytes = 2 * 8 * (BN / 8) * 2 * 4;  // two parities x one staging row per epilogue warp
   static constexpr int kTotal = kGnOffset + kGnBytes + 1024;   // +1024: manual 1 KiB alignment slack
 };
 
@@ -181,10 +181,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     const int w_i = r & (tw - 1);
     const int h_i = (r >> p.tw_log2) & (th - 1);
     const int n_i = r >> (p.tw_log2 + p.th_log2);
-    float* gn_w = gn_smem + warp * (BN / 8) * 2;         // this warp's staging row: [BN/8][2]
+    constexpr int kGnRow = (BN / 8) * 2;                 // floats per staging row: [BN/8][2]
+    int gn_par = 0;                                      // staging rows are double-buffered over tiles
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      float* gn_w = gn_smem + (gn_par * 8 + warp) * kGnRow;   // this warp's staging row for this tile
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int tx = m_tile % p.tiles_x;
@@ -293,15 +295,27 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       if (p.gn_partials != nullptr) {
+        // One 64-byte record [8 groups][sum, sumsq] per (M tile, sample slot): the eight warps' staging rows are
+        // folded in a fixed order by warp `slot` (a tile spans 1 << tn_log2 samples; quarter q belongs to slot
+        // q >> (2 - tn_log2)).  The rows of this parity are not touched again before the next-but-one tile, and
+        // every warp passes the barrier of the next tile in between, so one barrier per tile suffices.
         __syncwarp();
-        const int groups_in_tile = BN / p.group_size;
-        const int g0 = n0 / p.group_size;
-        float* dst = p.gn_partials + ((int64_t)((m_tile * 4 + q) * 2 + half) * 8) * 2;
-        for (int i = lane; i < groups_in_tile * 2; i += 32) {
-          const int g = g0 + (i >> 1);
-          if (g < 8) dst[g * 2 + (i & 1)] = gn_w[i];
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (warp < (1 << tn_log2)) {
+          const int groups_in_tile = BN / p.group_size;
+          const int g0 = n0 / p.group_size;
+          const int qshift = 2 - tn_log2;
+          float* dst = p.gn_partials + (((int64_t)m_tile << tn_log2) + warp) * 16;
+          for (int i = lane; i < groups_in_tile * 2; i += 32) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+              if (((w & 3) >> qshift) == warp) sum += gn_smem[(gn_par * 8 + w) * kGnRow + i];
+            const int g = g0 + (i >> 1);
+            if (g < 8) dst[g * 2 + (i & 1)] = sum;
+          }
         }
-        __syncwarp();
+        gn_par ^= 1;
       }
     }
   }
@@ -509,6 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTN + half * 128;
+      float gn_s = 0.f, gn_q = 0.f;
 
 #pragma unroll 1
       for (int cp = 0; cp < 2; ++cp) {                     // 64 pixels per staging pass
@@ -553,16 +568,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_t_kernel(const __grid_
               sum += __shfl_xor_sync(0xffffffffu, sum, o);
               sq += __shfl_xor_sync(0xffffffffu, sq, o);
             }
-            const int lanes_per_group = p.group_size >= 32 ? 32 : 16;
-            if ((lane & (lanes_per_group - 1)) == 0 && st < p.m_tiles) {
-              const int g = ch / p.group_size;
-              // entry layout shared with conv_igemm_kernel: [(tile*4 + pixel quarter)*2 + half][8][2]; this kernel
-              // produces whole-quarter sums, so the second half-entry is zero
-              float* dst = p.gn_partials + ((((int64_t)st * 4 + c) * 2) * 8 + g) * 2;
-              dst[0] = sum;
-              dst[1] = sq;
-              dst[16] = 0.f;
-              dst[17] = 0.f;
+            // record layout shared with conv_igemm_kernel: [M tile][sample slot][8 groups][2]; the four 32-pixel
+            // chunks of a sub-tile are accumulated in order and flushed when the sample slot changes
+            gn_s += sum;
+            gn_q += sq;
+            const int qshift = 2 - tn_log2;
+            if (c == 3 || ((c + 1) >> qshift) != (c >> qshift)) {
+              const int lanes_per_group = p.group_size >= 32 ? 32 : 16;
+              if ((lane & (lanes_per_group - 1)) == 0 && st < p.m_tiles) {
+                const int g = ch / p.group_size;
+                float* dst = p.gn_partials + (((((int64_t)st << tn_log2) + (c >> qshift)) * 8) + g) * 2;
+                dst[0] = gn_s;
+                dst[1] = gn_q;
+              }
+              gn_s = 0.f;
+              gn_q = 0.f;
             }
           }
           if (p.act == 1) {
@@ -777,7 +797,8 @@ using namespace srgd;
 
 extern "C" int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
-  return tile_geom(B, Ho, Wo).m_tiles;
+  const TileGeom g = tile_geom(B, Ho, Wo);
+  return g.m_tiles << g.tn_log2;                         // gn_partials records: one per (M tile, sample slot)
 }
 
 extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {

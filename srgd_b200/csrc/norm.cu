@@ -17,32 +17,28 @@ constexpr float kGnEps = 1e-5f;        // nn.GroupNorm default (model.py:247)
 constexpr int kGroups = 8;
 
 // ---- statistics ------------------------------------------------------------------------------
-// One block per sample: fold the conv-epilogue partial sums (conv_igemm.cu) in fp64.  An entry is the 64-byte
-// record [8 groups][sum, sumsq] of one (tile, pixel quarter, column half); thread t reads float4 number (t & 3)
-// of every 256th entry, so a warp touches 8 whole records per load instruction; 1024 threads x 8 loads keep the
-// whole 256 KB of a 256x256 sample in flight at once (the kernel is pure memory latency).
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials,
-                                                          float* __restrict__ stats, int H, int W, int C,
-                                                          TileGeom g) {
-  pdl_wait();
-  const int n = blockIdx.x;
-  const int tb = n >> g.tn_log2, n_i = n & ((1 << g.tn_log2) - 1);
+// Fold the conv-epilogue partial sums (conv_igemm.cu) of sample n in fp64, by a 256-thread block.  A record is the
+// 64 bytes [8 groups][sum, sumsq] of one (M tile, sample slot); thread t reads float4 number (t & 3) of every 64th
+// record, so a warp touches 8 whole records per load instruction.  A 256x256 sample has 512 records (32 KB, L2
+// resident: the conv wrote them last).  The summation order is fixed, so every block that folds the same sample
+// gets bit-identical statistics -- gn_apply_kernel relies on that to fold them redundantly in its prologue instead
+// of paying a separate launch.  out16 (shared): [8 groups][mean, rstd]; ends with a block barrier.
+__device__ __forceinline__ void gn_sample_stats(const float* __restrict__ partials, int n, const TileGeom& g,
+                                                double cnt, float* out16, double (*red)[4][4]) {
+  const int tb = n >> g.tn_log2, slot = n & ((1 << g.tn_log2) - 1);
   const int tiles_per_b = g.tiles_x * g.tiles_y;
-  const int warps_per_sample = 4 >> g.tn_log2;           // tn_log2 <= 2 (checked by the conv launcher)
-  const int per_tile = warps_per_sample * 2;             // two half-entries per (tile, pixel quarter)
-  const int entries = tiles_per_b * per_tile;
   const int part = threadIdx.x & 3;                      // groups 2*part, 2*part+1
   const float4* base = reinterpret_cast<const float4*>(partials) +
-                       ((int64_t)(tb * tiles_per_b) * 4 + n_i * warps_per_sample) * 2 * 4 + part;
+                       ((((int64_t)tb * tiles_per_b) << g.tn_log2) + slot) * 4 + part;
+  const int64_t rstride = (int64_t)4 << g.tn_log2;       // float4s between the records of consecutive tiles
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  constexpr int kU = 8;                                  // independent 16-byte loads in flight per thread
-  for (int e0 = threadIdx.x >> 2; e0 < entries; e0 += 256 * kU) {
+  constexpr int kU = 4;                                  // independent 16-byte loads in flight per thread
+  for (int t0 = threadIdx.x >> 2; t0 < tiles_per_b; t0 += 64 * kU) {
     float4 v[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int e = e0 + u * 256;
-      // entry e -> tile e / per_tile, slot e % per_tile; records of one tile are 8 entries (4 quarters x 2) apart
-      v[u] = e < entries ? __ldg(base + ((int64_t)(e / per_tile) * 8 + (e % per_tile)) * 4) : make_float4(0, 0, 0, 0);
+      const int t = t0 + u * 64;
+      v[u] = t < tiles_per_b ? __ldg(base + t * rstride) : make_float4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) { a0 += v[u].x; a1 += v[u].y; a2 += v[u].z; a3 += v[u].w; }
@@ -55,21 +51,31 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
     a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     a3 += __shfl_xor_sync(0xffffffffu, a3, o);
   }
-  __shared__ double sh[32][4][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < 4) { sh[warp][lane][0] = a0; sh[warp][lane][1] = a1; sh[warp][lane][2] = a2; sh[warp][lane][3] = a3; }
+  if (lane < 4) { red[warp][lane][0] = a0; red[warp][lane][1] = a1; red[warp][lane][2] = a2; red[warp][lane][3] = a3; }
   __syncthreads();
   if (threadIdx.x < kGroups) {
     const int grp = threadIdx.x, pt = grp >> 1, o = (grp & 1) * 2;
-    double s = 0.0, q = 0.0;
-    for (int w = 0; w < 32; ++w) { s += sh[w][pt][o]; q += sh[w][pt][o + 1]; }
-    const double cnt = (double)H * W * (C / kGroups);
-    const double mean = s / cnt;
+    double sum = 0.0, q = 0.0;
+    for (int w = 0; w < 8; ++w) { sum += red[w][pt][o]; q += red[w][pt][o + 1]; }
+    const double mean = sum / cnt;
     double var = q / cnt - mean * mean;                  // biased variance, as nn.GroupNorm
     if (var < 0.0) var = 0.0;
-    stats[(n * kGroups + grp) * 2] = (float)mean;
-    stats[(n * kGroups + grp) * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+    out16[grp * 2] = (float)mean;
+    out16[grp * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
   }
+  __syncthreads();
+}
+
+// Stand-alone form (tests, callers that want the statistics): one block per sample -> stats[B][8][2].
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partials,
+                                                         float* __restrict__ stats, int H, int W, int C,
+                                                         TileGeom g) {
+  __shared__ double red[8][4][4];
+  __shared__ float st16[16];
+  pdl_wait();
+  gn_sample_stats(partials, blockIdx.x, g, (double)H * W * (C / kGroups), st16, red);
+  if (threadIdx.x < 16) stats[blockIdx.x * 16 + threadIdx.x] = st16[threadIdx.x];
 }
 
 // Stand-alone statistics over a bf16 NHWC tensor: one block per (sample, group).
@@ -115,15 +121,18 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 // 256 vectors) and keeps its affine coefficients -- and the final-conv weights -- in registers: no shared-memory
 // traffic and no block barrier.
 template <bool HAS_RES, int INV_LANES, bool FINAL, bool REG, int U>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
                                                        const bf16* residual, bf16* y, float* __restrict__ inv_out,
                                                        const float* __restrict__ fin_w, const float* __restrict__ fin_b,
-                                                       float* __restrict__ eps, int HW, int C, int reverse) {
+                                                       float* __restrict__ eps, int HW, int C, int reverse,
+                                                       const float* __restrict__ partials, TileGeom geom) {
   extern __shared__ float sm[];                          // !REG: A[C] | B[C] | (FINAL: fin_w[3][C])
-  pdl_wait();                                            // stats come from the preceding gn_finalize launch
+  __shared__ double red[8][4][4];
+  __shared__ float st16[16];
+  pdl_wait();                                            // partials / stats come from the preceding launch
   float* sA = sm;
   float* sB = sm + C;
   float* sW = sm + 2 * C;
@@ -157,10 +166,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* x, int Bx, co
   };
   if (i < total) issue(i);
 
+  // statistics: either given (stats[B][8][2]) or folded here from the producer conv's partial records
+  if (partials != nullptr) {
+    gn_sample_stats(partials, bs, geom, (double)HW * G, st16, red);
+  } else {
+    if (threadIdx.x < 16) st16[threadIdx.x] = stats[bs * 16 + threadIdx.x];
+    __syncthreads();
+  }
   float ra[8], rb[8], rw[24];
   auto coef = [&](int c, float& a, float& bb) {
-    const float mean = stats[(bs * kGroups + c / G) * 2];
-    const float rstd = stats[(bs * kGroups + c / G) * 2 + 1];
+    const float mean = st16[(c / G) * 2];
+    const float rstd = st16[(c / G) * 2 + 1];
     a = rstd * gamma[c];
     bb = beta[c] - mean * a;
     if (scale_shift != nullptr) {
@@ -337,6 +353,18 @@ static int gn_reverse() {
   return cached;
 }
 
+// CTAs per SM the gn_apply grid is capped at.  Every CTA pays the statistics fold + coefficient set-up once, so with
+// fused statistics the grid is one resident wave (4 CTAs of 256 threads and <= 64 registers per SM) and each thread
+// streams many vectors; SRGD_GN_CTAS_PER_SM overrides (A/B knob).
+static int gn_ctas_per_sm() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("SRGD_GN_CTAS_PER_SM");
+    cached = (e != nullptr && atoi(e) > 0) ? atoi(e) : 4;
+  }
+  return cached;
+}
+
 static int stream_grid(int64_t items_per_block_total, int ctas_per_sm) {
   int64_t cap = (int64_t)sm_count() * ctas_per_sm;
   if (items_per_block_total < 1) items_per_block_total = 1;
@@ -355,8 +383,8 @@ extern "C" int srgd_groupnorm_finalize(const float* gn_partials, float* stats, i
                "groupnorm_finalize: bad arguments");
   const TileGeom g = tile_geom(B, H, W);
   SRGD_REQUIRE(g.tn_log2 <= 2, "groupnorm_finalize: needs H*W >= 32");
-  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)g.m_tiles * 8 * 8 * 2 * 4, as_stream(stream));
-  SRGD_CUDA_OK(launch_k(gn_finalize_kernel, dim3(B), dim3(1024), 0, as_stream(stream), gn_partials, stats, H, W, C, g));
+  ProfScope prof(SRGD_PK_NORM_MISC, 0.0, (double)(g.m_tiles << g.tn_log2) * 8 * 2 * 4, as_stream(stream));
+  SRGD_CUDA_OK(launch_k(gn_finalize_kernel, dim3(B), dim3(256), 0, as_stream(stream), gn_partials, stats, H, W, C, g));
   count_launch();
   return SRGD_OK;
 }
@@ -373,19 +401,24 @@ extern "C" int srgd_groupnorm_stats(const void* x, float* stats, int32_t B, int3
   return SRGD_OK;
 }
 
-extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gamma,
-                                    const float* beta, const float* scale_shift, int64_t ss_stride,
+extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const float* gn_partials,
+                                    const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                                     const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
                                     int32_t C, srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  SRGD_REQUIRE(x && stats && gamma && beta && y, "groupnorm_apply: null argument");
+  SRGD_REQUIRE(x && gamma && beta && y, "groupnorm_apply: null argument");
+  SRGD_REQUIRE((stats != nullptr) != (gn_partials != nullptr),
+               "groupnorm_apply: pass exactly one of stats / gn_partials");
+  const TileGeom geom = tile_geom(Bx, H, W);             // geometry of the conv launch that produced the partials
+  SRGD_REQUIRE(gn_partials == nullptr || geom.tn_log2 <= 2, "groupnorm_apply: gn_partials need H*W >= 32");
   SRGD_REQUIRE(B > 0 && Bx > 0 && Bx <= B && H > 0 && W > 0 && C > 0 && C % 64 == 0 && C <= 4096,
                "groupnorm_apply: bad shape B=%d Bx=%d H=%d W=%d C=%d", B, Bx, H, W, C);
   SRGD_REQUIRE(B <= 65535, "groupnorm_apply: B too large");
   const int64_t total = (int64_t)H * W * (C / 8);
   int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
-  if ((int64_t)gx * B > (int64_t)sm_count() * 16) gx = (sm_count() * 16 + B - 1) / B;
+  const int cap = sm_count() * gn_ctas_per_sm();
+  if ((int64_t)gx * B > cap) gx = (cap + B - 1) / B;
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 2 * sizeof(float);
   const bf16* xr = reinterpret_cast<const bf16*>(x);
@@ -400,7 +433,7 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
 #define SRGD_GN_LAUNCH(RES, INV, R)                                                                              \
   SRGD_CUDA_OK(launch_k(gn_apply_kernel<RES, INV, false, R, 2>, grid, dim3(256), R ? 0 : smem, cst, xr, Bx,       \
                         stats, gamma, beta, scale_shift, ss_stride, rr, yr, inv_out, nullptr, nullptr, nullptr,   \
-                        H * W, C, gn_reverse()))
+                        H * W, C, gn_reverse(), gn_partials, geom))
   if (inv_out != nullptr && C == 128) SRGD_GN_LAUNCH(true, 16, true);
   else if (inv_out != nullptr) SRGD_GN_LAUNCH(true, 32, true);
   else if (residual && reg) SRGD_GN_LAUNCH(true, 0, true);
@@ -412,18 +445,23 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   return SRGD_OK;
 }
 
-extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gamma, const float* beta,
+extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, const float* gn_partials,
+                                          const float* gamma, const float* beta,
                                           const void* residual, const float* final_w, const float* final_b,
                                           float* eps, int32_t B, int32_t H, int32_t W, int32_t C,
                                           srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  SRGD_REQUIRE(x && stats && gamma && beta && residual && final_w && final_b && eps, "groupnorm_apply_final: null argument");
+  SRGD_REQUIRE(x && gamma && beta && residual && final_w && final_b && eps, "groupnorm_apply_final: null argument");
+  SRGD_REQUIRE((stats != nullptr) != (gn_partials != nullptr),
+               "groupnorm_apply_final: pass exactly one of stats / gn_partials");
+  const TileGeom geom = tile_geom(B, H, W);
   SRGD_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && C == 128 && (H * W) % 2 == 0,
                "groupnorm_apply_final: needs C == 128 and an even pixel count (B=%d H=%d W=%d C=%d)", B, H, W, C);
   const int64_t total = (int64_t)H * W * (C / 8);
   int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
-  if ((int64_t)gx * B > (int64_t)sm_count() * 16) gx = (sm_count() * 16 + B - 1) / B;
+  const int cap = sm_count() * gn_ctas_per_sm();
+  if ((int64_t)gx * B > cap) gx = (cap + B - 1) / B;
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 5 * sizeof(float);
   ProfScope prof(SRGD_PK_GN_APPLY, 2.0 * B * H * W * C * 3, (double)B * H * W * (C * 4.0 + 12.0), as_stream(stream));
@@ -431,7 +469,7 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
   SRGD_CUDA_OK(launch_k(gn_apply_kernel<true, 0, true, true, 2>, grid, dim3(256), 0, as_stream(stream),
                         reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0,
                         reinterpret_cast<const bf16*>(residual), nullptr, nullptr, final_w, final_b, eps, H * W, C,
-                        gn_reverse()));
+                        gn_reverse(), gn_partials, geom));
   count_launch();
   return SRGD_OK;
 }

@@ -290,34 +290,34 @@ struct Fwd {
     run((conv_impl & 1) ? srgd_conv_direct(&d, st) : srgd_conv_igemm(&d, st));
   }
 
-  // conv3x3 + GroupNorm statistics -> stats[B][8][2]
+  // conv3x3 whose epilogue leaves the GroupNorm partial records in `part` (debug paths: statistics in `stats`)
   void conv_gn(const void* a0, int c0, const void* a1, int c1, int H, int W, const void* w, const float* bias, int cout,
-               void* out, float* stats) {
-    const int mt = tile_geom(B, H, W).m_tiles;
-    float* part = reinterpret_cast<float*>(alloc((size_t)mt * 8 * 8 * 2 * sizeof(float)));
+               void* out, float* part, float* stats) {
     conv(a0, c0, a1, c1, H, W, 3, w, bias, cout, out, part, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC);
-    if (!dry && ok()) {
-      if (conv_impl & 3) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
-      else run(srgd_groupnorm_finalize(part, stats, B, H, W, cout, st));
-    }
-    ar.release(part);
+    if (!dry && ok() && (conv_impl & 3)) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
   }
 
   // ResnetBlock (model.py:261-285).  Consumes nothing; returns a fresh [B][H][W][cout] buffer.
   // inv_out (optional): receives 1/||row|| of the block output for the attention block that follows.
   // eps_out (optional, last block of the network only): the final 1x1 conv is fused into the second GroupNorm pass
   // (srgd_groupnorm_apply_final); the block output is then not materialised and nullptr is returned.
+  // GroupNorm statistics never get a launch of their own on the product path: the conv epilogue writes one
+  // 64-byte partial record per 128-pixel tile and every block of the apply kernel folds its sample's records.
   void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr,
                  float* eps_out = nullptr) {
     const size_t M = (size_t)B * H * W;
+    const bool fused_stats = !(conv_impl & 3);
     void* c1 = alloc(M * r.cout * 2);
     float* stats = reinterpret_cast<float*>(alloc((size_t)B * 8 * 2 * sizeof(float)));
-    conv_gn(xa, r.cin0, xb, r.cin1, H, W, r.c1_w, r.c1_b, r.cout, c1, stats);
+    float* part = reinterpret_cast<float*>(alloc((size_t)srgd_conv_m_tiles(B, H, W) * 8 * 2 * sizeof(float)));
+    const float* st_arg = fused_stats ? nullptr : stats;
+    const float* pt_arg = fused_stats ? part : nullptr;
+    conv_gn(xa, r.cin0, xb, r.cin1, H, W, r.c1_w, r.c1_b, r.cout, c1, part, stats);
     if (!dry && ok())
-      run(srgd_groupnorm_apply(c1, B, stats, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, nullptr, B, H, W,
-                               r.cout, st));
+      run(srgd_groupnorm_apply(c1, B, st_arg, pt_arg, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, nullptr,
+                               B, H, W, r.cout, st));
     void* c2 = alloc(M * r.cout * 2);
-    conv_gn(c1, r.cout, nullptr, 0, H, W, r.c2_w, r.c2_b, r.cout, c2, stats);
+    conv_gn(c1, r.cout, nullptr, 0, H, W, r.c2_w, r.c2_b, r.cout, c2, part, stats);
     ar.release(c1);
     const void* resid = xa;
     void* rbuf = nullptr;
@@ -329,16 +329,19 @@ struct Fwd {
     }
     if (eps_out != nullptr) {
       if (!dry && ok())
-        run(srgd_groupnorm_apply_final(c2, stats, r.n2_g, r.n2_b, resid, u.final_w, u.final_b, eps_out, B, H, W, r.cout,
-                                       st));
+        run(srgd_groupnorm_apply_final(c2, st_arg, pt_arg, r.n2_g, r.n2_b, resid, u.final_w, u.final_b, eps_out, B, H,
+                                       W, r.cout, st));
       ar.release(rbuf);
+      ar.release(part);
       ar.release(stats);
       ar.release(c2);
       return nullptr;
     }
     if (!dry && ok())
-      run(srgd_groupnorm_apply(c2, B, stats, r.n2_g, r.n2_b, nullptr, 0, resid, c2, inv_out, B, H, W, r.cout, st));
+      run(srgd_groupnorm_apply(c2, B, st_arg, pt_arg, r.n2_g, r.n2_b, nullptr, 0, resid, c2, inv_out, B, H, W, r.cout,
+                               st));
     ar.release(rbuf);
+    ar.release(part);
     ar.release(stats);
     tap(r.name, c2, M * r.cout * 2);
     return c2;

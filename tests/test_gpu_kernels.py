@@ -252,8 +252,8 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
     ss = torch.randn(B, 2 * C + 7, generator=g) * 0.3             # row stride != 2C on purpose
     resid = G.bf16_round(torch.randn(B, C, H, W, generator=g))
-    mt = lib.srgd_conv_m_tiles(B, H, W)
-    part = torch.full((mt * 8 * 8 * 2,), float("nan"), device="cuda")
+    mt = lib.srgd_conv_m_tiles(B, H, W)                           # 64-byte records: one per (M tile, sample slot)
+    part = torch.full((mt * 8 * 2,), float("nan"), device="cuda")
     out = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
     d = G.plain_conv_desc([G.nhwc_bf16(x)], G.pack_conv_weight(w), B, H, W, C, 3, out, bias=bias.cuda(),
                           gn_partials=part)
@@ -277,7 +277,7 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     yd = torch.empty_like(out)
     want_inv = C in (128, 256) and (H * W) % 4 == 0                          # fused RMSNorm statistic (model.py:207)
     inv = torch.full((B * H * W,), float("nan"), device="cuda") if want_inv else None
-    _lib.check(lib.srgd_groupnorm_apply(G.P(out), B, G.P(stats), G.P(gamma.cuda()), G.P(beta.cuda()),
+    _lib.check(lib.srgd_groupnorm_apply(G.P(out), B, G.P(stats), None, G.P(gamma.cuda()), G.P(beta.cuda()),
                                         G.P(ss.cuda()), 2 * C + 7, G.P(G.nhwc_bf16(resid)), G.P(yd), G.P(inv),
                                         B, H, W, C, G.stream()))
     torch.cuda.synchronize()
@@ -285,6 +285,15 @@ def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     if want_inv:
         ref_inv = 1.0 / yd.float().reshape(B * H * W, C).norm(dim=1).clamp(min=1e-12)
         torch.testing.assert_close(inv, ref_inv, rtol=1e-5, atol=1e-7)
+    # product path: no finalize launch, every block folds the partial records itself -- bit-identical result
+    yd2 = torch.empty_like(out)
+    _lib.check(lib.srgd_groupnorm_apply(G.P(out), B, None, G.P(part), G.P(gamma.cuda()), G.P(beta.cuda()),
+                                        G.P(ss.cuda()), 2 * C + 7, G.P(G.nhwc_bf16(resid)), G.P(yd2), None,
+                                        B, H, W, C, G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(yd2, yd)
+    assert lib.srgd_groupnorm_apply(G.P(out), B, G.P(stats), G.P(part), G.P(gamma.cuda()), G.P(beta.cuda()), None, 0,
+                                    None, G.P(yd2), None, B, H, W, C, G.stream()) != 0      # exactly one of the two
 
 
 def test_groupnorm_apply_final_fused_conv(lib):
@@ -299,7 +308,7 @@ def test_groupnorm_apply_final_fused_conv(lib):
     stats = torch.empty(B * 8 * 2, device="cuda")
     _lib.check(lib.srgd_groupnorm_stats(G.P(xd), G.P(stats), B, H, W, C, G.stream()))
     eps = torch.full((B, 3, H, W), float("nan"), device="cuda")
-    _lib.check(lib.srgd_groupnorm_apply_final(G.P(xd), G.P(stats), G.P(gamma.cuda()), G.P(beta.cuda()),
+    _lib.check(lib.srgd_groupnorm_apply_final(G.P(xd), G.P(stats), None, G.P(gamma.cuda()), G.P(beta.cuda()),
                                               G.P(G.nhwc_bf16(res)), G.P(w3.cuda().contiguous()), G.P(b3.cuda()), G.P(eps),
                                               B, H, W, C, G.stream()))
     torch.cuda.synchronize()
