@@ -60,6 +60,8 @@ struct alignas(64) ConvKernelParams {
   float* gn_partials;
 };
 
+constexpr int kMaxBiasSmem = 2048;   // widest conv of the U-Net (pixel-shuffle 1024 -> 2048)
+
 template <int BN, int STAGES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * kBK * 2;
@@ -68,7 +70,8 @@ struct ConvSmem {
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr, gn staging
   static constexpr int kGnOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;
   static constexpr int kGnBytes = 2 * 8 * (BN / 8) * 2 * 4;  // two parities x one staging row per epilogue warp
-  static constexpr int kTotal = kGnOffset + kGnBytes + 1024;   // +1024: manual 1 KiB alignment slack
+  static constexpr int kBiasOffset = kGnOffset + kGnBytes;   // the whole bias vector (Cout <= kMaxBiasSmem floats)
+  static constexpr int kTotal = kBiasOffset + kMaxBiasSmem * 4 + 1024;   // +1024: manual 1 KiB alignment slack
 };
 
 template <int BN, int STAGES>
@@ -83,10 +86,18 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* gn_smem = reinterpret_cast<float*>(smem + L::kGnOffset);
+  float* bias_smem = reinterpret_cast<float*>(smem + L::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * BN;                 // 128 / 256 / 512: powers of two >= 32
+
+  // The bias vector is read by every epilogue chunk: a global load there is a ~500-clock long-scoreboard stall per
+  // chunk (ncu source view of the short-K launches: 30 % of all samples); staged once, it is a broadcast LDS.
+  // Weights are never written by a kernel, so this may precede pdl_wait().
+  const bool bias_staged = p.bias != nullptr && p.Cout <= kMaxBiasSmem;
+  if (bias_staged)
+    for (int i = threadIdx.x; i < p.Cout; i += kThreads) bias_smem[i] = __ldg(p.bias + i);
 
   if (warp == kTmaWarp && lane == 0) {
     for (int i = 0; i < p.n_src; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
@@ -205,6 +216,15 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         __syncwarp();
       }
 
+      // residual rows are requested one chunk ahead (and the first one before the accumulator is even complete):
+      // a load issued where it is consumed is a full memory latency on the epilogue's critical path
+      const bool has_res = p.residual != nullptr && valid && p.out_mode != SRGD_OUT_PIXEL_SHUFFLE;
+      uint4 rres[4];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rres[j] = ld_stream(p.residual + pix * p.Cout + n0 + half * 32 + j * 8);
+      }
+
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -218,7 +238,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
-        if (p.bias != nullptr) {
+        if (bias_staged) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_smem + nc + j);
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        } else if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + j));
@@ -275,13 +301,17 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           } else {
             off = pix * p.Cout + nc;
           }
-          if (p.residual != nullptr) {
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float rr[8];
-              unpack8(ld_stream(p.residual + off + j), rr);
+              unpack8(rres[j >> 3], rr);
 #pragma unroll
               for (int t = 0; t < 8; ++t) f[j + t] += rr[t];
+            }
+            if (c + 2 < BN / 32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rres[j] = ld_stream(p.residual + off + 64 + j * 8);   // chunk c + 2
             }
           }
 #pragma unroll
@@ -757,8 +787,10 @@ static int validate_desc(const srgd_conv_desc* d) {
   }
   SRGD_REQUIRE(d->Ktot % 64 == 0, "conv: Ktot must be a multiple of 64");
   SRGD_REQUIRE(d->out_mode == SRGD_OUT_BF16_NHWC || d->out_mode == SRGD_OUT_PIXEL_SHUFFLE, "conv: bad out_mode");
-  if (d->out_mode == SRGD_OUT_PIXEL_SHUFFLE)
+  if (d->out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
     SRGD_REQUIRE(d->Cout % 128 == 0, "conv: pixel-shuffle output needs Cout %% 128 == 0");
+    SRGD_REQUIRE(d->residual == nullptr, "conv: a residual cannot be combined with the pixel-shuffle output mode");
+  }
   return SRGD_OK;
 }
 

@@ -581,15 +581,15 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
       const float tot = ssq + ptx::lds_f32(ssq_addr + ((half ^ 1) * 128 + row) * 4);
       const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
       bf16* orow = p.out + px * C + half * 64;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {                     // unrolled: xr[] must be indexed statically (registers)
         uint32_t v[32];
         ptx::tmem_ld_32x32(tb + 128 + half * 64 + cc * 32, v);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float r[8], o[8];
-          unpack8(cc == 0 ? xr[jj] : xr[4 + jj], r);
+          unpack8(xr[cc * 4 + jj], r);
           const float4 b0 = ptx::lds_f4(bias_addr + (cc * 32 + jj * 8) * 4);
           const float4 b1 = ptx::lds_f4(bias_addr + (cc * 32 + jj * 8 + 4) * 4);
           const float4 g0 = ptx::lds_f4(gain_addr + (cc * 32 + jj * 8) * 4);

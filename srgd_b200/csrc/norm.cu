@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx,
 #pragma unroll
         for (int o = INV_LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if ((threadIdx.x & (INV_LANES - 1)) == 0)
-          inv_out[(int64_t)b * HW + iu / vec_per_pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+          inv_out[(int64_t)b * HW + iu / vec_per_pix] = fminf(rsqrtf(ss), 1e12f);   // = 1 / max(sqrt(ss), 1e-12)
       }
     }
     i += U * stride;
