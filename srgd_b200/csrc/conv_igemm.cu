@@ -194,6 +194,16 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     const int n_i = r >> (p.tw_log2 + p.th_log2);
     constexpr int kGnRow = (BN / 8) * 2;                 // floats per staging row: [BN/8][2]
     int gn_par = 0;                                      // staging rows are double-buffered over tiles
+    // Register copies of the parameters the chunk loop uses.  Left to itself the compiler re-reads them from the
+    // constant bank inside the loop (LDC, long scoreboard: 7 % of the samples of the short-K launches); the empty
+    // asm pins them.
+    int Cout = p.Cout, Ho = p.Ho, Wo = p.Wo, act = p.act, out_mode = p.out_mode, group_size = p.group_size;
+    bf16* outp = p.out;
+    const bf16* resp = p.residual;
+    float* gnp = p.gn_partials;
+    asm volatile("" : "+r"(Cout), "+r"(Ho), "+r"(Wo), "+r"(act), "+r"(out_mode), "+r"(group_size));
+    asm volatile("" : "+l"(outp), "+l"(resp), "+l"(gnp));
+    const uint32_t bias_addr = ptx::smem_u32(bias_smem);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -206,23 +216,23 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       const int x = (tx << p.tw_log2) + w_i;
       const int y = (ty << p.th_log2) + h_i;
       const int b = (tb << tn_log2) + n_i;
-      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-      const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+      const bool valid = (x < Wo) && (y < Ho) && (b < p.B);
+      const int64_t pix = ((int64_t)b * Ho + y) * Wo + x;
       const int n0 = n_tile * BN;
       const float rs = (p.row_scale != nullptr && valid) ? p.row_scale[pix] : 1.0f;
 
-      if (p.gn_partials != nullptr) {
+      if (gnp != nullptr) {
         for (int i = lane; i < (BN / 8) * 2; i += 32) gn_w[i] = 0.f;
         __syncwarp();
       }
 
       // residual rows are requested one chunk ahead (and the first one before the accumulator is even complete):
       // a load issued where it is consumed is a full memory latency on the epilogue's critical path
-      const bool has_res = p.residual != nullptr && valid && p.out_mode != SRGD_OUT_PIXEL_SHUFFLE;
+      const bool has_res = resp != nullptr && valid && out_mode != SRGD_OUT_PIXEL_SHUFFLE;
       uint4 rres[4];
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rres[j] = ld_stream(p.residual + pix * p.Cout + n0 + half * 32 + j * 8);
+        for (int j = 0; j < 4; ++j) rres[j] = ld_stream(resp + pix * Cout + n0 + half * 32 + j * 8);
       }
 
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -241,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         if (bias_staged) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias_smem + nc + j);
+            const float4 bv = ptx::lds_f4(bias_addr + (nc + j) * 4);       // explicit ld.shared (a generic LD is a long-scoreboard op)
             f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
           }
         } else if (p.bias != nullptr) {
@@ -251,7 +261,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
           }
         }
-        if (p.gn_partials != nullptr) {
+        if (gnp != nullptr) {
           // per 8-channel sub-block sums over this warp's 32 pixels (masked rows contribute 0)
           float s8[4], q8[4];
 #pragma unroll
@@ -266,11 +276,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             s8[sb] = s;
             q8[sb] = qq;
           }
-          if (p.group_size >= 32) {                      // whole chunk lies in one group
+          if (group_size >= 32) {                      // whole chunk lies in one group
             float s = warp_sum(s8[0] + s8[1] + s8[2] + s8[3]);
             float qq = warp_sum(q8[0] + q8[1] + q8[2] + q8[3]);
             if (lane == 0) {
-              const int g = (c * 32) / p.group_size;     // group index local to this tile
+              const int g = (c * 32) / group_size;     // group index local to this tile
               gn_w[g * 2] += s;
               gn_w[g * 2 + 1] += qq;
             }
@@ -280,26 +290,26 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
               float s = warp_sum(s8[sb]);
               float qq = warp_sum(q8[sb]);
               if (lane == 0) {
-                const int g = (c * 32 + sb * 8) / p.group_size;
+                const int g = (c * 32 + sb * 8) / group_size;
                 gn_w[g * 2] += s;
                 gn_w[g * 2 + 1] += qq;
               }
             }
           }
         }
-        if (p.act == 1) {
+        if (act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) silu2(f[j], f[j + 1]);
         }
-        if (valid && nc < p.Cout) {
+        if (valid && nc < Cout) {
           int64_t off;
-          if (p.out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
-            const int cq = p.Cout >> 2;                  // C' output channels
+          if (out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
+            const int cq = Cout >> 2;                  // C' output channels
             const int sub = nc / cq;                     // (i*2 + j) sub-pixel
             const int cc = nc - sub * cq;
-            off = (((int64_t)b * (2 * p.Ho) + (2 * y + (sub >> 1))) * (2 * p.Wo) + (2 * x + (sub & 1))) * cq + cc;
+            off = (((int64_t)b * (2 * Ho) + (2 * y + (sub >> 1))) * (2 * Wo) + (2 * x + (sub & 1))) * cq + cc;
           } else {
-            off = pix * p.Cout + nc;
+            off = pix * Cout + nc;
           }
           if (has_res) {
 #pragma unroll
@@ -311,11 +321,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
             if (c + 2 < BN / 32) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) rres[j] = ld_stream(p.residual + off + 64 + j * 8);   // chunk c + 2
+              for (int j = 0; j < 4; ++j) rres[j] = ld_stream(resp + off + 64 + j * 8);   // chunk c + 2
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) st_stream(p.out + off + j, pack8(f + j));
+          for (int j = 0; j < 32; j += 8) st_stream(outp + off + j, pack8(f + j));
         }
       }
       // accumulator fully read: hand it back to the MMA warp
@@ -324,7 +334,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      if (p.gn_partials != nullptr) {
+      if (gnp != nullptr) {
         // One 64-byte record [8 groups][sum, sumsq] per (M tile, sample slot): the eight warps' staging rows are
         // folded in a fixed order by warp `slot` (a tile spans 1 << tn_log2 samples; quarter q belongs to slot
         // q >> (2 - tn_log2)).  The rows of this parity are not touched again before the next-but-one tile, and
@@ -332,10 +342,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         __syncwarp();
         asm volatile("bar.sync 3, 256;" ::: "memory");
         if (warp < (1 << tn_log2)) {
-          const int groups_in_tile = BN / p.group_size;
-          const int g0 = n0 / p.group_size;
+          const int groups_in_tile = BN / group_size;
+          const int g0 = n0 / group_size;
           const int qshift = 2 - tn_log2;
-          float* dst = p.gn_partials + (((int64_t)m_tile << tn_log2) + warp) * 16;
+          float* dst = gnp + (((int64_t)m_tile << tn_log2) + warp) * 16;
           for (int i = lane; i < groups_in_tile * 2; i += 32) {
             float sum = 0.f;
 #pragma unroll

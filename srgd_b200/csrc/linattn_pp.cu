@@ -513,15 +513,16 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
     const int n_g = (ntiles + 1 - g) >> 1;
     const float sqrt_c = 11.313708498984761f;              // sqrt(128)
 
-    float inv_next = n_g > 0 ? p.inv[row0 + (int64_t)g * 128 + row] : 0.f;   // fetched one tile ahead
     for (int it = 0; it < n_g; ++it) {
       const uint32_t par = it & 1;
       const int64_t px = row0 + (int64_t)(2 * it + g) * 128 + row;
-      const float my_invl = inv_next * kPpLog2e;
-      if (it + 1 < n_g) inv_next = p.inv[px + 256];
+      // requested before the wait for this tile's Q: the load latency hides behind it (a value prefetched one
+      // tile ahead lived in a register across the whole body and was spilled -- ncu: 9 % of the samples at its reload)
+      const float my_inv = p.inv[px];
       // ---- q: softmax over the 32 channels of each head (model.py:315); 1/||x|| folded into the exponent ----
       ptx::mbar_wait(&q_full[g], par);
       ptx::tc_fence_after();
+      const float my_invl = my_inv * kPpLog2e;
 #pragma unroll 1
       for (int i = 0; i < 2; ++i) {
         uint32_t v[32];
@@ -582,18 +583,18 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
       const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
       bf16* orow = p.out + px * C + half * 64;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {                     // unrolled: xr[] must be indexed statically (registers)
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tb + 128 + half * 64 + cc * 32, v);
+      for (int cc = 0; cc < 4; ++cc) {                     // unrolled (xr[] stays in registers); 16 columns at a time
+        uint32_t v[16];                                    // keeps the live set under the 96-register cap of 576 threads
+        ptx::tmem_ld_32x16(tb + 128 + half * 64 + cc * 16, v);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 2; ++jj) {
           float r[8], o[8];
-          unpack8(xr[cc * 4 + jj], r);
-          const float4 b0 = ptx::lds_f4(bias_addr + (cc * 32 + jj * 8) * 4);
-          const float4 b1 = ptx::lds_f4(bias_addr + (cc * 32 + jj * 8 + 4) * 4);
-          const float4 g0 = ptx::lds_f4(gain_addr + (cc * 32 + jj * 8) * 4);
-          const float4 g1 = ptx::lds_f4(gain_addr + (cc * 32 + jj * 8 + 4) * 4);
+          unpack8(xr[cc * 2 + jj], r);
+          const float4 b0 = ptx::lds_f4(bias_addr + (cc * 16 + jj * 8) * 4);
+          const float4 b1 = ptx::lds_f4(bias_addr + (cc * 16 + jj * 8 + 4) * 4);
+          const float4 g0 = ptx::lds_f4(gain_addr + (cc * 16 + jj * 8) * 4);
+          const float4 g1 = ptx::lds_f4(gain_addr + (cc * 16 + jj * 8 + 4) * 4);
           o[0] = fmaf(__uint_as_float(v[jj * 8 + 0]) + b0.x, scale * g0.x, r[0]);
           o[1] = fmaf(__uint_as_float(v[jj * 8 + 1]) + b0.y, scale * g0.y, r[1]);
           o[2] = fmaf(__uint_as_float(v[jj * 8 + 2]) + b0.z, scale * g0.z, r[2]);
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
           o[5] = fmaf(__uint_as_float(v[jj * 8 + 5]) + b1.y, scale * g1.y, r[5]);
           o[6] = fmaf(__uint_as_float(v[jj * 8 + 6]) + b1.z, scale * g1.z, r[6]);
           o[7] = fmaf(__uint_as_float(v[jj * 8 + 7]) + b1.w, scale * g1.w, r[7]);
-          st_stream(orow + cc * 32 + jj * 8, pack8(o));
+          st_stream(orow + cc * 16 + jj * 8, pack8(o));
         }
       }
       ptx::tc_fence_before();
