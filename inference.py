@@ -40,6 +40,9 @@ def parse_args(argv=None):
     # multi-GPU sharding of the file list (defaults come from torchrun's environment)
     ap.add_argument('--world_size', type=int, default=int(os.environ.get('WORLD_SIZE', 1)))
     ap.add_argument('--rank', type=int, default=int(os.environ.get('RANK', 0)))
+    # throughput extension: consecutive files of equal size are sampled together (their tiles share denoiser batches);
+    # every image still sees the noise stream of its own reseeded run, so the outputs do not change
+    ap.add_argument('--images_per_batch', type=int, default=1)
     return ap.parse_args(argv)
 
 
@@ -65,13 +68,15 @@ def _to_image(t: torch.Tensor) -> Image.Image:
     return Image.fromarray(arr, mode='RGB')
 
 
-def sr_target_image(image, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
-                    class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
-                    num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71):
-    width, height = image.size
+def sr_target_images(images, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
+                     class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
+                     num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71):
+    """The per-image pipeline of the reference (inference.py:59-98) for a list of equally sized PIL images."""
+    width, height = images[0].size
+    assert all(im.size == (width, height) for im in images)
     # the reference maps both 'bicubic' and 'lanczos' to bicubic (inference.py:66-69)
-    upscaled = image.resize((width * scale, height * scale), resample=Image.BICUBIC)
-    condition_x = _to_unit_tensor(upscaled).to(sr_model.device)
+    condition_x = torch.cat([_to_unit_tensor(im.resize((width * scale, height * scale), resample=Image.BICUBIC))
+                             for im in images]).to(sr_model.device)
     label = None if test_label is None else torch.tensor([test_label], dtype=torch.long, device=sr_model.device)
     seed_everything(seed)
     with torch.inference_mode():
@@ -81,9 +86,13 @@ def sr_target_image(image, sr_model, scale=4, batch_size=8, test_label=2, cond_s
                                        class_guidance_start_steps=class_guidance_start_steps,
                                        generation_start_steps=generation_start_steps,
                                        num_sample_steps=num_sample_steps, amp=enable_amp)
-    sr_img = _to_image(output[0])
-    assert sr_img.size == (width * 4, height * 4)
-    return sr_img
+    outs = [_to_image(o) for o in output]
+    assert all(o.size == (width * 4, height * 4) for o in outs)
+    return outs
+
+
+def sr_target_image(image, sr_model, **kw):
+    return sr_target_images([image], sr_model, **kw)[0]
 
 
 def try_open_image(image_path):
@@ -96,10 +105,23 @@ def try_open_image(image_path):
 def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0,
                            guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
                            generation_start_steps=0, num_sample_steps=250, start_index=0, end_index=None,
-                           enable_amp=False, interpolation='bicubic', seed=71, world_size=1, rank=0):
+                           enable_amp=False, interpolation='bicubic', seed=71, world_size=1, rank=0,
+                           images_per_batch=1):
     print(f"save images at: {output_dir}")
     os.makedirs(output_dir, exist_ok=True)
     files = sorted(glob.glob(f"{input_dir}/*"))[start_index:end_index][rank::world_size]
+    kw = dict(scale=scale, batch_size=batch_size, test_label=test_label, cond_scale=cond_scale,
+              guidance_start_steps=guidance_start_steps, class_cond_scale=class_cond_scale,
+              class_guidance_start_steps=class_guidance_start_steps, generation_start_steps=generation_start_steps,
+              num_sample_steps=num_sample_steps, enable_amp=enable_amp, interpolation=interpolation, seed=seed)
+    pending = []                                   # (image, save_path) of consecutive equally sized inputs
+
+    def flush():
+        if pending:
+            for out, (_, save_path) in zip(sr_target_images([im for im, _ in pending], sr_model, **kw), pending):
+                out.save(save_path)
+            pending.clear()
+
     for path in files:
         save_path = os.path.join(output_dir, os.path.basename(path).replace('.png', '_out.png'))
         if os.path.exists(save_path):           # doubles as resume-after-crash (inference.py:126)
@@ -109,11 +131,10 @@ def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=
         if image is None:
             print('Invalid image or unable to open image:', path)
             continue
-        sr_target_image(image, sr_model, scale=scale, batch_size=batch_size, test_label=test_label,
-                        cond_scale=cond_scale, guidance_start_steps=guidance_start_steps,
-                        class_cond_scale=class_cond_scale, class_guidance_start_steps=class_guidance_start_steps,
-                        generation_start_steps=generation_start_steps, num_sample_steps=num_sample_steps,
-                        enable_amp=enable_amp, interpolation=interpolation, seed=seed).save(save_path)
+        if pending and (image.size != pending[0][0].size or len(pending) >= images_per_batch):
+            flush()
+        pending.append((image, save_path))
+    flush()
 
 
 def main(argv=None):
@@ -137,7 +158,8 @@ def main(argv=None):
                            generation_start_steps=args.generation_start_steps,
                            num_sample_steps=args.num_sample_steps, start_index=args.start_index,
                            end_index=args.end_index, enable_amp=args.amp, interpolation=args.interpolation,
-                           seed=args.seed, world_size=args.world_size, rank=args.rank)
+                           seed=args.seed, world_size=args.world_size, rank=args.rank,
+                           images_per_batch=max(1, args.images_per_batch))
 
 
 if __name__ == '__main__':

@@ -284,20 +284,32 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
                      start_white_noise=True, amp=False, shard_tiles=False):
         """`shard_tiles=True` (extension): with an initialised torch.distributed group the tiles of every step are
         split over the ranks and exchanged once per step; every rank returns the same image, bit-identical to the
-        single-GPU result (srgd_b200/tiled.py)."""
+        single-GPU result (srgd_b200/tiled.py).
+
+        `condition_x` with a batch of N > 1 same-sized images (extension; the reference's loop only works for N = 1):
+        the images advance together, their tiles stacked into one denoiser batch, and share ONE noise stream -- the
+        result equals N consecutive single-image calls each preceded by the same reseed, which is what the reference
+        CLI does (inference.py:81)."""
         num_sample_steps = self.num_sample_steps if num_sample_steps is None else num_sample_steps
         _lib.require_cuda(condition_x, "tiled_sample")
         condition_x = condition_x * 2 - 1
         batch, ch, h, w = condition_x.shape
         plan = TilePlan(h, w, tile_size, tile_stride)
         condition_x = F.pad(condition_x, plan.canvas_pad, mode='reflect')
+        one = (1,) + tuple(condition_x.shape[1:])
+
+        def shared(noise):                                                      # one draw, used by every image
+            return noise if batch == 1 else noise.expand(batch, -1, -1, -1).contiguous()
+
         if generation_start_steps > 0:
             start = 1. - generation_start_steps / num_sample_steps
-            img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32))
+            img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32),
+                                   noise=shared(self._randn(one, self.device)))
         elif start_white_noise:
-            img = self._randn(condition_x.shape, self.device)                   # RNG draw #0 (model.py:3311)
+            img = shared(self._randn(one, self.device))                         # RNG draw #0 (model.py:3311)
         else:
-            img, _ = self.q_sample(condition_x, torch.tensor(1., dtype=torch.float32))
+            img, _ = self.q_sample(condition_x, torch.tensor(1., dtype=torch.float32),
+                                   noise=shared(self._randn(one, self.device)))
         top, bottom, left, right = plan.crop
         images = [img[:, :, top:bottom, left:right].clone().cpu()] if with_images else None
         x0_images = [img[:, :, top:bottom, left:right].clone().cpu()] if with_x0_images else None

@@ -105,16 +105,29 @@ def _all_gather_tiles(local: Optional[torch.Tensor], counts: List[int], shape_ta
 def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan, steps: torch.Tensor,
               num_sample_steps: int, batch_size: int, class_label, cond_scale: float, guidance_start_steps: int,
               class_cond_scale: float, class_guidance_start_steps: int, generation_start_steps: int,
-              x_start: Optional[torch.Tensor] = None, on_step=None, group=None, shard: bool = False):
-    """The sampling loop of tiled_sample (model.py:3345-3401) on an initial noise canvas `img` [1,3,H,W] and the
+              x_start: Optional[torch.Tensor] = None, on_step=None, group=None, shard: bool = False,
+              max_rows: int = 64):
+    """The sampling loop of tiled_sample (model.py:3345-3401) on an initial noise canvas `img` [N,3,H,W] and the
     hull-masked condition canvas.  Updates and returns `img` (and `x_start` if given).  With `shard=True` and an
-    initialised process group the minibatches of every step are split over the ranks (see module docstring)."""
+    initialised process group the minibatches of every step are split over the ranks (see module docstring).
+
+    N > 1 (extension; the reference's loop only works for N = 1): N images of the same size advance together and
+    SHARE the noise stream, which is exactly what N consecutive runs of the reference CLI produce -- it reseeds every
+    generator before each image (inference.py:81).  The tiles of a minibatch are stacked image-major into one
+    denoiser batch of at most `max_rows` rows, so the 4-tile odd steps of a small image still fill the GPU."""
     tile = plan.tile_size
     world = dist.get_world_size(group) if (shard and dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     dev = img.device
+    n_img = img.shape[0]
     # the condition tiles of the two grids never change: gather them once per minibatch
     cond_cache = {}
+
+    def gather_all(canvas, chunk, lo, hi):
+        if hi - lo == 1:
+            return ops.gather(canvas[lo:lo + 1], chunk, tile)
+        return torch.cat([ops.gather(canvas[k:k + 1], chunk, tile) for k in range(lo, hi)], 0)
+
     for i in range(num_sample_steps):
         if i < generation_start_steps:
             continue
@@ -128,22 +141,36 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
             noise = None if last else ops.randn((len(chunk), img.shape[1], tile, tile), dev)
             if ci % world != rank:
                 continue
-            key = (i % 2, ci)
-            if key not in cond_cache:
-                cond_cache[key] = ops.gather(cond_canvas, chunk, tile)
-            xt = ops.gather(img, chunk, tile)
-            out, x0 = ops.p_sample(xt, steps[i], cond_cache[key], class_label, cs, ccs, steps[i + 1], noise)
-            mine_out.append(out)
-            mine_x0.append(x0)
+            per_call = max(1, max_rows // len(chunk))          # images per denoiser call
+            outs, x0s = [], []
+            for lo in range(0, n_img, per_call):
+                hi = min(n_img, lo + per_call)
+                key = (i % 2, ci, lo)
+                if key not in cond_cache:
+                    cond_cache[key] = gather_all(cond_canvas, chunk, lo, hi)
+                xt = gather_all(img, chunk, lo, hi)
+                nz = noise if (noise is None or hi - lo == 1) else noise.repeat(hi - lo, 1, 1, 1)
+                out, x0 = ops.p_sample(xt, steps[i], cond_cache[key], class_label, cs, ccs, steps[i + 1], nz)
+                outs.append(out)
+                x0s.append(x0)
+            # [n_img * len(chunk), ...] image-major
+            mine_out.append(outs[0] if len(outs) == 1 else torch.cat(outs, 0))
+            mine_x0.append(x0s[0] if len(x0s) == 1 else torch.cat(x0s, 0))
             mine_idx.append(ci)
+
+        def scatter_all(canvas, coords, stack):
+            n = len(coords)
+            for k in range(n_img):
+                ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
+
         if world == 1:
             for ci, out, x0 in zip(mine_idx, mine_out, mine_x0):
-                ops.scatter(img, chunks[ci], out, tile)
+                scatter_all(img, chunks[ci], out)
                 if x_start is not None:
-                    ops.scatter(x_start, chunks[ci], x0, tile)
+                    scatter_all(x_start, chunks[ci], x0)
         else:
             # exchange step: every rank contributes the tiles it wrote; all replicas apply all of them
-            counts = [sum(len(chunks[ci]) for ci in range(r, len(chunks), world)) for r in range(world)]
+            counts = [n_img * sum(len(chunks[ci]) for ci in range(r, len(chunks), world)) for r in range(world)]
             tail = (img.shape[1], tile, tile)
             local = torch.cat(mine_out, 0) if mine_out else None
             gathered = _all_gather_tiles(local, counts, tail, dev, img.dtype, group)
@@ -152,15 +179,20 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
                 local0 = torch.cat(mine_x0, 0) if mine_x0 else None
                 gathered_x0 = _all_gather_tiles(local0, counts, tail, dev, img.dtype, group)
             for r in range(world):
-                coords_r = [c for ci in range(r, len(chunks), world) for c in chunks[ci]]
-                if coords_r:
-                    ops.scatter(img, coords_r, gathered[r], tile)
+                pos = 0
+                for ci in range(r, len(chunks), world):
+                    n = n_img * len(chunks[ci])
+                    scatter_all(img, chunks[ci], gathered[r][pos:pos + n])
                     if gathered_x0 is not None:
-                        ops.scatter(x_start, coords_r, gathered_x0[r], tile)
+                        scatter_all(x_start, chunks[ci], gathered_x0[r][pos:pos + n])
+                    pos += n
         if i % 2 == 1:
             # outside the hull of the shifted grid the state is replaced by fresh noise at the next noise level
             # (q_sample of zeros, model.py:3392-3396); the draw covers the whole canvas like the reference's
-            ops.renoise_outside(img, ops.randn(tuple(img.shape), dev), ops.sigma(steps[i + 1]), plan.inner)
+            fresh = ops.randn((1,) + tuple(img.shape[1:]), dev)
+            sig = ops.sigma(steps[i + 1])
+            for k in range(n_img):
+                ops.renoise_outside(img[k:k + 1], fresh, sig, plan.inner)
         if on_step is not None:
             on_step(i, img, x_start)
     return img, x_start

@@ -90,6 +90,18 @@ def main():
             if rank == 0:
                 print(f"{name}: tiled_sample() {lr}x{lr} LR on {world} GPU(s), minibatch {bs}: {per:.2f} ms/step (mean of "
                       f"even+odd grids) -> {1 / (per * 250e-3):.4f} images/s", flush=True)
+        # configs[4] as a many-image workload: N 128x128-LR images advance together (tiles of different images share
+        # the denoiser batches, run_tiled's N > 1 extension)
+        if world == 1:
+            for nimg in (4, 16):
+                c = torch.cat([synth(128, k) for k in range(nimg)]).cuda()
+                diff.tiled_sample(batch_size=9, condition_x=c, class_label=label, num_sample_steps=250,
+                                  generation_start_steps=248)
+                ms = timed(lambda: diff.tiled_sample(batch_size=9, condition_x=c, class_label=label,
+                                                     num_sample_steps=250, generation_start_steps=250 - n))
+                per = ms / n
+                print(f"configs[4] x{nimg} images per batch: {per:.2f} ms/step -> {nimg / (per * 250e-3):.4f} images/s",
+                      flush=True)
     if world > 1:
         dist.destroy_process_group()
 

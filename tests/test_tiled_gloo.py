@@ -113,3 +113,39 @@ def test_run_tiled_sharded_over_gloo_is_bit_identical(world):
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
         assert torch.equal(ret[r], ref), f"rank {r} differs from the single-process reference"
+
+
+def _multi_image_path(sd, conds01, label, max_rows, nsteps):
+    """N same-sized images advanced together (run_tiled's N > 1 extension): shared noise stream, stacked minibatches."""
+    gen = torch.Generator().manual_seed(71)
+    cond = conds01 * 2 - 1
+    plan = TilePlan(cond.shape[2], cond.shape[3], TILE, TILE)
+    cond = F.pad(cond, plan.canvas_pad, mode="reflect")
+    img = torch.randn((1,) + tuple(cond.shape[1:]), generator=gen).repeat(cond.shape[0], 1, 1, 1)
+    it, ib, il, ir = plan.inner
+    cond_canvas = torch.zeros_like(cond)
+    cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
+    steps = torch.linspace(1., 0., nsteps + 1)
+    img, _ = run_tiled(TorchOps(sd, gen), img, cond_canvas, plan, steps, nsteps, BATCH, label, 1.0, 0, 2.0, 0, 0,
+                       max_rows=max_rows)
+    top, bottom, left, right = plan.crop
+    return (img[:, :, top:bottom, left:right].clamp(-1, 1) + 1) * 0.5
+
+
+@pytest.mark.parametrize("max_rows", [4, 64])
+def test_run_tiled_many_images_equal_consecutive_single_runs(max_rows):
+    """Two images of one size in one run == two runs of one image each, every run reseeded with the same seed (what the
+    reference CLI does per image, inference.py:81).  max_rows = 4 forces one image per denoiser call."""
+    torch.set_num_threads(4)
+    nsteps = 3
+    sd = O.make_state_dict(SPEC, 11)
+    g = torch.Generator().manual_seed(13)
+    conds01 = torch.rand(2, 3, 104, 120, generator=g)
+    label = torch.tensor([2])
+    together = _multi_image_path(sd, conds01, label, max_rows, nsteps)
+    for k in range(2):
+        alone = O.tiled_sample(sd, SPEC, BATCH, conds01[k:k + 1], label, class_cond_scale=2.0, num_sample_steps=nsteps,
+                               tile_size=TILE, tile_stride=TILE, generator=torch.Generator().manual_seed(71))
+        # rows of a stacked denoiser batch are independent, but the CPU conv blocks differently per batch size and the
+        # first steps amplify by 1/alpha: compare to 5e-4
+        torch.testing.assert_close(together[k:k + 1], alone, rtol=0, atol=5e-4)   # (a logic error would be O(0.1))
