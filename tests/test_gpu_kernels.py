@@ -125,6 +125,8 @@ CONV_CASES = [
     (1, 6, 256, [128], 128, 3),           # W % 256 == 0: halo-reuse variant (row-shifted tcgen05 operand descriptors)
     (2, 3, 512, [64, 128], 128, 3),       # halo reuse over a concat, two 256-pixel tiles per row
     (1, 2, 256, [64], 384, 3),            # halo reuse, three 128-channel slabs
+    (1, 160, 128, [64], 256, 3),          # 160 tiles on 148 SMs: the 12 tail tiles run as 128-column halves
+    (1, 152, 128, [128], 512, 1),         # tail split with two n-tiles per pixel tile (304 tiles, 8 split)
 ]
 
 
@@ -241,7 +243,8 @@ def test_init_conv_pack_and_7tap(lib):
 # ------------------------------------------------------------------------------------------------
 # GroupNorm / RMSNorm
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64), (2, 4, 256, 128)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 8, 8, 1024), (1, 64, 64, 256), (2, 16, 16, 64), (2, 4, 256, 128),
+                                     (1, 160, 128, 256)])      # last: tail-split tiles (160 tiles on 148 SMs)
 def test_groupnorm_fused_stats_and_apply(lib, conv_variant, B, H, W, C):
     g = torch.Generator().manual_seed(C + H)
     Cin = 128
