@@ -222,6 +222,28 @@ def test_config1_vs_reference_golden():
     assert img.shape == ref.shape and p >= 45.0
 
 
+def test_config3_cfg_vs_reference_golden():
+    """Classifier-free guidance end to end against the UNMODIFIED reference on the CPU (fp32): `sample()` at batch 1,
+    test_label 2, class_cond_scale 3.0 -- two sequential U-Net calls per step there (model.py:3151-3154), ONE 2x-batch
+    launch sequence + the guidance combine fused into the sampler update here -- full 250-step schedule, seed 71,
+    same noise stream (tests/golden/make_golden_config3.py).  Bar: final-image PSNR >= 45 dB."""
+    from PIL import Image
+    g = load("config3_full")
+    spec = O.UnetSpec()
+    diff = make_diffusion(spec, O.make_state_dict(spec, 1234, init="torch"), 256, int(g["steps"]))
+    diff.rng_device = "cpu"
+    hr = Image.fromarray(g["lr"], mode="RGB").resize((256, 256), resample=Image.BICUBIC)
+    cond01 = torch.from_numpy(np.array(hr, dtype=np.uint8)).permute(2, 0, 1).float().div(255.)[None]
+    torch.manual_seed(int(g["seed"]))
+    img = diff.sample(batch_size=1, condition_x=cond01.cuda(), class_label=torch.tensor([int(g["label"])]).cuda(),
+                      class_cond_scale=float(g["ccs"]), num_sample_steps=int(g["steps"])).cpu()
+    ref = T(g["img"])
+    p = G.psnr(img, ref)
+    print(f"config 3 / CFG {float(g['ccs'])} (reference CPU fp32 vs B200 bf16, {int(g['steps'])} steps): PSNR {p:.2f} dB, "
+          f"max-abs {float((img - ref).abs().max()):.4f}")
+    assert img.shape == ref.shape and p >= 45.0
+
+
 def test_launch_count_reported():
     diff, sd, spec = build("full")
     x = torch.randn(1, 3, 64, 64, device="cuda")
