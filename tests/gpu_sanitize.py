@@ -1,0 +1,40 @@
+"""compute-sanitizer driver (not a pytest test): two p_sample steps of a dim-64 U-Net on a 128x64 tile batch of 2 with
+classifier-free guidance -- every kernel family of the hot path (both conv kernels incl. the halo variant is skipped at
+this width, fused linear attention, tcgen05 flash attention, GroupNorm apply with folded statistics, sampler update).
+
+    compute-sanitizer --tool memcheck  python tests/gpu_sanitize.py
+    compute-sanitizer --tool racecheck python tests/gpu_sanitize.py
+    compute-sanitizer --tool synccheck python tests/gpu_sanitize.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import srgd_oracle as O  # noqa: E402  (deterministic random-init weights only)
+import model as M  # noqa: E402
+
+
+def main():
+    dim = int(os.environ.get("SAN_DIM", "128"))
+    H, W = int(os.environ.get("SAN_H", "64")), int(os.environ.get("SAN_W", "256"))
+    spec = O.UnetSpec(dim=dim)
+    unet = M.ConditionalSRUnet(dim=dim, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=H, num_sample_steps=250)
+    diff.load_state_dict(O.make_state_dict(spec, 5), strict=True)
+    diff = diff.eval().to("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, H, W, generator=g).cuda()
+    cond = (torch.rand(2, 3, H, W, generator=g) * 2 - 1).cuda()
+    steps = torch.linspace(1., 0., 251)
+    with torch.inference_mode():
+        for i in (100, 101):
+            x, _ = diff.p_sample(x, steps[i], cond, torch.tensor([1], device="cuda"), 1.0, 3.0, steps[i + 1])
+    torch.cuda.synchronize()
+    print("sanitize run finished:", float(x.abs().mean()), diff.last_step_launches, "launches per step")
+
+
+if __name__ == "__main__":
+    main()
