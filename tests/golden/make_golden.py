@@ -2,7 +2,7 @@
 
 Run in the build container only (the reference does not travel to the GPU box):
 
-    PYTHONPATH=oracle/_shim:/root/reference python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # GOLDEN_OUT=/tmp/g to write elsewhere
 
 Weights come from oracle.srgd_oracle.make_state_dict(spec, seed) and are loaded into the
 reference modules with load_state_dict(strict=True) -- which also pins the 280-key checkpoint
@@ -17,8 +17,12 @@ import torch
 warnings.filterwarnings("ignore")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, ROOT)
-import model as ref                                   # /root/reference/model.py (via PYTHONPATH)
+OUT = os.environ.get("GOLDEN_OUT", HERE)              # write somewhere else to check the committed fixtures reproduce
+sys.path.insert(0, "/root/reference")                 # the reference's model.py must win over the repo-root drop-in
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_shim"))
+sys.path.append(ROOT)
+import model as ref
+assert os.path.realpath(ref.__file__).startswith("/root/reference/"), ref.__file__
 from oracle import srgd_oracle as O
 
 torch.set_num_threads(os.cpu_count())
@@ -48,7 +52,7 @@ def build_ref(spec, seed, image_size, steps=250):
 
 def save(name, **arrs):
     out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
 
@@ -78,7 +82,7 @@ def main():
         geo.append(dict(hw=(h, w), coord=coord, pad=pad, n0=len(c0), n1=len(c1), c0=c0, c1=c1,
                         area=area, apad=apad))
     import json
-    with open(os.path.join(HERE, "geometry.json"), "w") as f:
+    with open(os.path.join(OUT, "geometry.json"), "w") as f:
         json.dump(geo, f)
 
     # ---- U-Net forward goldens ----
