@@ -169,3 +169,36 @@ def test_inference_cli_flags():
     a = inference.parse_args(["-c", "x", "-m", "w", "--input_dir", "i", "--output_dir", "o", "--class_cond_scale", "3.0",
                               "--test_label", "2", "--seed", "5", "--no_amp"])
     assert a.class_cond_scale == 3.0 and a.test_label == 2 and a.seed == 5 and a.amp is False
+
+
+def test_inference_directory_loop_groups_equal_sizes(tmp_path, capsys):
+    """The CLI's directory loop (reference inference.py:108-142) with --images_per_batch: consecutive equally sized
+    inputs are sampled together, outputs are named <name>_out.png at 4x, existing outputs and unreadable files are
+    skipped -- checked on the CPU with a stand-in for the sampler."""
+    import numpy as np
+    from PIL import Image
+    import inference
+
+    class Stub:
+        device = torch.device("cpu")
+        calls = []
+
+        def tiled_sample(self, batch_size, condition_x, **kw):
+            Stub.calls.append(tuple(condition_x.shape))
+            return torch.zeros_like(condition_x)
+
+    in_dir, out_dir = tmp_path / "in", tmp_path / "out"
+    in_dir.mkdir()
+    out_dir.mkdir()
+    rs = np.random.RandomState(0)
+    for name, (w, h) in {"a.png": (10, 8), "b.png": (10, 8), "c.png": (10, 8), "d.png": (12, 8), "e.png": (10, 8)}.items():
+        Image.fromarray(rs.randint(0, 256, (h, w, 3), dtype=np.uint8), mode="RGB").save(in_dir / name)
+    (in_dir / "bad.png").write_bytes(b"nope")
+    Image.new("RGB", (40, 32)).save(out_dir / "e_out.png")                      # already done -> skipped
+    inference.batch_sr_target_images(str(in_dir), str(out_dir), Stub(), num_sample_steps=2, images_per_batch=2)
+    out = capsys.readouterr().out
+    assert "skip" in out and "Invalid image" in out
+    # a,b together; c alone (batch full); d alone (different size)
+    assert Stub.calls == [(2, 3, 32, 40), (1, 3, 32, 40), (1, 3, 32, 48)]
+    assert sorted(os.listdir(out_dir)) == ["a_out.png", "b_out.png", "c_out.png", "d_out.png", "e_out.png"]
+    assert Image.open(out_dir / "d_out.png").size == (48, 32)

@@ -149,3 +149,42 @@ def test_run_tiled_many_images_equal_consecutive_single_runs(max_rows):
         # rows of a stacked denoiser batch are independent, but the CPU conv blocks differently per batch size and the
         # first steps amplify by 1/alpha: compare to 5e-4
         torch.testing.assert_close(together[k:k + 1], alone, rtol=0, atol=5e-4)   # (a logic error would be O(0.1))
+
+
+def _multi_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sd = O.make_state_dict(SPEC, 11)
+        g = torch.Generator().manual_seed(13)
+        conds01 = torch.rand(2, 3, 104, 120, generator=g)
+        gen = torch.Generator().manual_seed(71)
+        cond = conds01 * 2 - 1
+        plan = TilePlan(cond.shape[2], cond.shape[3], TILE, TILE)
+        cond = F.pad(cond, plan.canvas_pad, mode="reflect")
+        img = torch.randn((1,) + tuple(cond.shape[1:]), generator=gen).repeat(2, 1, 1, 1)
+        it, ib, il, ir = plan.inner
+        cond_canvas = torch.zeros_like(cond)
+        cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
+        steps = torch.linspace(1., 0., 3)
+        img, _ = run_tiled(TorchOps(sd, gen), img, cond_canvas, plan, steps, 2, BATCH, torch.tensor([2]), 1.0, 0, 2.0, 0,
+                           0, shard=(world > 1), max_rows=64)
+        ret[rank] = img.clone()
+        if world > 1:
+            dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_run_tiled_many_images_sharded_over_gloo():
+    """Two images advancing together with the minibatches of every step split over two gloo ranks: both replicas end
+    with the canvases of the single-process run (same stacked batches per minibatch -> bit-identical)."""
+    ret = mp.Manager().dict()
+    mp.spawn(_multi_worker, args=(1, _free_port(), ret), nprocs=1, join=True)
+    single = ret[0]
+    ret2 = mp.Manager().dict()
+    mp.spawn(_multi_worker, args=(2, _free_port(), ret2), nprocs=2, join=True)
+    for r in range(2):
+        assert torch.equal(ret2[r], single), f"rank {r} differs from the single-process run"
