@@ -71,7 +71,8 @@ struct ConvSmem {
   static constexpr int kGnOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;
   static constexpr int kGnBytes = 2 * 8 * (BN / 8) * 2 * 4;  // two parities x one staging row per epilogue warp
   static constexpr int kBiasOffset = kGnOffset + kGnBytes;   // the whole bias vector (Cout <= kMaxBiasSmem floats)
-  static constexpr int kTotal = kBiasOffset + kMaxBiasSmem * 4 + 1024;   // +1024: manual 1 KiB alignment slack
+  static constexpr int kStoreOffset = kBiasOffset + kMaxBiasSmem * 4;   // per epilogue warp: 32 rows x 64 B transpose tile
+  static constexpr int kTotal = kStoreOffset + 8 * 2048 + 1024;          // +1024: manual 1 KiB alignment slack
 };
 
 template <int BN, int STAGES>
@@ -204,6 +205,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     asm volatile("" : "+r"(Cout), "+r"(Ho), "+r"(Wo), "+r"(act), "+r"(out_mode), "+r"(group_size));
     asm volatile("" : "+l"(outp), "+l"(resp), "+l"(gnp));
     const uint32_t bias_addr = ptx::smem_u32(bias_smem);
+    // Output stores go through a per-warp 32 x 64 B transpose tile: a thread owns one pixel row, so storing its 64 B
+    // directly makes every store instruction touch 32 different lines (the L1 store path bounds the short-K convs);
+    // read back transposed, four lanes cover one row's 64 B and an instruction touches 8 lines.  16-byte pieces
+    // are XOR-swizzled by (row >> 1) & 3, which keeps both directions free of bank conflicts.
+    const uint32_t stile = ptx::smem_u32(smem + L::kStoreOffset) + warp * 2048;
+    const int srow = lane >> 2, spiece = lane & 3;         // read-back role: row 8k + srow, piece spiece
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -220,6 +227,20 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       const int64_t pix = ((int64_t)b * Ho + y) * Wo + x;
       const int n0 = n_tile * BN;
       const float rs = (p.row_scale != nullptr && valid) ? p.row_scale[pix] : 1.0f;
+      // element offsets of the four rows this lane writes back (channel 0 of the pixel; pixel-shuffle: of its 2x2 block)
+      int64_t sbase[4];
+      bool svalid[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rk = q * 32 + 8 * k + srow;
+        const int xk = (tx << p.tw_log2) + (rk & (tw - 1));
+        const int yk = (ty << p.th_log2) + ((rk >> p.tw_log2) & (th - 1));
+        const int bk = (tb << tn_log2) + (rk >> (p.tw_log2 + p.th_log2));
+        svalid[k] = (xk < Wo) && (yk < Ho) && (bk < p.B);
+        sbase[k] = (out_mode == SRGD_OUT_PIXEL_SHUFFLE)
+                       ? (((int64_t)bk * (2 * Ho) + 2 * yk) * (2 * Wo) + 2 * xk) * (Cout >> 2)
+                       : (((int64_t)bk * Ho + yk) * Wo + xk) * Cout;
+      }
 
       if (gnp != nullptr) {
         for (int i = lane; i < (BN / 8) * 2; i += 32) gn_w[i] = 0.f;
@@ -301,32 +322,41 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) silu2(f[j], f[j + 1]);
         }
-        if (valid && nc < Cout) {
-          int64_t off;
-          if (out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
-            const int cq = Cout >> 2;                  // C' output channels
-            const int sub = nc / cq;                     // (i*2 + j) sub-pixel
-            const int cc = nc - sub * cq;
-            off = (((int64_t)b * (2 * Ho) + (2 * y + (sub >> 1))) * (2 * Wo) + (2 * x + (sub & 1))) * cq + cc;
-          } else {
-            off = pix * Cout + nc;
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float rr[8];
+            unpack8(rres[j >> 3], rr);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[j + t] += rr[t];
           }
-          if (has_res) {
+          if (c + 2 < BN / 32) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float rr[8];
-              unpack8(rres[j >> 3], rr);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) f[j + t] += rr[t];
-            }
-            if (c + 2 < BN / 32) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rres[j] = ld_stream(resp + off + 64 + j * 8);   // chunk c + 2
-            }
+            for (int j = 0; j < 4; ++j) rres[j] = ld_stream(resp + pix * Cout + nc + 64 + j * 8);   // chunk c + 2
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) st_stream(outp + off + j, pack8(f + j));
         }
+        // channel offset of this chunk inside a row (pixel-shuffle: plus the sub-pixel's displacement)
+        int64_t coff;
+        if (out_mode == SRGD_OUT_PIXEL_SHUFFLE) {
+          const int cq = Cout >> 2;                      // C' output channels
+          const int sub = nc / cq;                       // (i*2 + j) sub-pixel
+          coff = ((int64_t)(sub >> 1) * (2 * Wo) + (sub & 1)) * cq + (nc - sub * cq);
+        } else {
+          coff = nc;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 pk = pack8(f + 8 * j);
+          ptx::sts_v4(stile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rl = 8 * k + srow;
+          const uint4 pk = ptx::lds_v4(stile + rl * 64 + ((spiece ^ ((rl >> 1) & 3)) << 4));
+          if (svalid[k]) st_stream(outp + sbase[k] + coff + spiece * 8, pk);
+        }
+        __syncwarp();                                    // the tile is rewritten by the next chunk
       }
       // accumulator fully read: hand it back to the MMA warp
       ptx::tc_fence_before();
