@@ -225,18 +225,18 @@ def main():
         # Every step's x / cond come from pinned host memory and its img_next goes back to pinned host memory inside
         # the timed region.  The copies run on a second stream, double-buffered: step k+1's inputs travel while step k
         # computes and step k's result travels while step k+1 computes (what a serving loop around p_sample does);
-        # the host waits for (= can read) the result of step k-1 before it issues step k+1.
+        # the host waits for (= can read) the result of step k-2 before it issues step k+1.
         e2e_steps = max(3, args.steps)                    # as long as the device-resident run: same clock / power state
         x_host = torch.randn(B, 3, TILE, TILE).pin_memory()
         c_host = (cond01 * 2 - 1).pin_memory()
-        r_host = [torch.empty(B, 3, TILE, TILE).pin_memory() for _ in range(2)]
+        r_host = [torch.empty(B, 3, TILE, TILE).pin_memory() for _ in range(3)]
         xd = [torch.empty(B, 3, TILE, TILE, device=dev) for _ in range(2)]
         cd = [torch.empty(B, 3, TILE, TILE, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream()
         h2d_done = [torch.cuda.Event() for _ in range(2)]
         comp_done = [torch.cuda.Event() for _ in range(2)]
-        d2h_done = [torch.cuda.Event() for _ in range(2)]
+        d2h_done = [torch.cuda.Event() for _ in range(3)]
 
         def issue_h2d(slot):
             with torch.cuda.stream(copy_stream):
@@ -245,12 +245,25 @@ def main():
                 cd[slot].copy_(c_host, non_blocking=True)
                 h2d_done[slot].record(copy_stream)
 
+        # One process per GPU: pipelined copies were measured erratic with several ranks on one box (15.1-18.3 ms per
+        # step at 2 GPUs against 14.9 device-resident, cause not found), so ranks > 1 keep the plain sequence
+        # copy in -> step -> copy out -> sync, which costs the ~0.8 ms of PCIe time per step but is stable.
+        pipelined = (world == 1) if not os.environ.get("SRGD_E2E_PIPELINED") else os.environ["SRGD_E2E_PIPELINED"] == "1"
         barrier()
         for ev in comp_done:
             ev.record(cur)
         e0.record()
-        issue_h2d(0)
-        for k in range(e2e_steps):
+        if not pipelined:
+            for k in range(e2e_steps):
+                i = (args.warmup + k) % SAMPLE_STEPS
+                xd[0].copy_(x_host, non_blocking=True)
+                cd[0].copy_(c_host, non_blocking=True)
+                o, _ = diff.p_sample(xd[0], steps[i], cd[0], label, 1.0, ccs, steps[i + 1])
+                r_host[0].copy_(o, non_blocking=True)
+                cur.synchronize()
+        else:
+            issue_h2d(0)
+        for k in range(e2e_steps if pipelined else 0):
             slot = k & 1
             i = (args.warmup + k) % SAMPLE_STEPS
             cur.wait_event(h2d_done[slot])
@@ -261,15 +274,20 @@ def main():
                 issue_h2d(slot ^ 1)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(comp_done[slot])
-                r_host[slot].copy_(o, non_blocking=True)
-                d2h_done[slot].record(copy_stream)
-            if k >= 1:
-                d2h_done[slot ^ 1].synchronize()                 # result of step k-1 is in host memory
-        d2h_done[(e2e_steps - 1) & 1].synchronize()
+                r_host[k % 3].copy_(o, non_blocking=True)
+                d2h_done[k % 3].record(copy_stream)
+            if k >= 2:
+                d2h_done[(k - 2) % 3].synchronize()              # result of step k-2 is in host memory (its buffer is
+                                                                 # rewritten by step k+1); two steps stay queued
+        for ev in d2h_done:
+            ev.synchronize()
         cur.wait_stream(copy_stream)
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
+        if os.environ.get("SRGD_BENCH_DEBUG"):
+            print(f"\n[rank {rank}] e2e {e2e_ms / e2e_steps:.3f} ms/step, device-resident {elapsed_ms / args.steps:.3f}\n",
+                  file=sys.stderr, flush=True)
         if world > 1:
             t = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,7 +364,7 @@ def main():
         e2e=dict(value=e2e_img_per_sec, unit="images/s", h2d_bytes_per_step=2 * B * 3 * TILE * TILE * 4,
                  d2h_bytes_per_step=B * 3 * TILE * TILE * 4, steps=e2e_steps,
                  call="ConditionalContinuousTimeGaussianDiffusionSR.p_sample with pinned host x/cond in, img_next out; "
-                      "copies double-buffered on a second stream"),
+                      + ("copies double-buffered on a second stream" if pipelined else "copy in, step, copy out, sync")),
         gpu_launches=int(step_launches) * args.steps + 1,
         roofline=roof, hbm_kernels=hbm,
         kernel_ms_per_step={k: round(v["ms"], 4) for k, v in prof.items()},
