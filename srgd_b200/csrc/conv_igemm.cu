@@ -11,10 +11,12 @@
 // the 128-byte-swizzled K-major layout tcgen05.mma consumes.  A channel concat (model.py:713-722)
 // is just more phases reading a second source: the cat is never materialised.
 //
-// Kernel organisation (persistent, one CTA per SM, 256 threads):
-//   warps 0..7    : epilogue      (tcgen05.ld 32x32b, row_scale, bias, GroupNorm partial sums, SiLU,
-//                                  residual, bf16 store in NHWC or pixel-shuffled NHWC); two warps per
-//                                  TMEM lane quarter, each taking every other 32-column chunk
+// Kernel organisation (persistent, one CTA per SM, 384 threads):
+//   warps 0..7    : epilogue      (tcgen05.ld 32x32b, row_scale, bias from shared memory, GroupNorm partial
+//                                  sums pre-reduced to one record per tile, SiLU, residual prefetched a chunk
+//                                  ahead, bf16 store in NHWC or pixel-shuffled NHWC through a per-warp
+//                                  transpose tile); two warps per TMEM lane quarter, each taking every other
+//                                  32-column chunk
 //   warp 8 lane 0 : TMA producer  (STAGES-deep smem ring, full/empty mbarriers)
 //   warp 9 lane 0 : MMA issuer    (4 x tcgen05.mma K=16 per 64-wide k-block; commit -> empty barrier)
 //   warp 10       : TMEM allocator (2 accumulator stages of BN fp32 columns)
