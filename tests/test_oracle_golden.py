@@ -151,3 +151,28 @@ def test_config1_full_size_three_steps(golden_dir):
     img = O.tiled_sample(sd, spec, int(g["batch_size"]), cond01, torch.tensor([int(g["label"])]),
                          num_sample_steps=int(g["steps"]))
     torch.testing.assert_close(img[..., ::2, ::2], T(g["img_sub2"]), rtol=0, atol=5e-4)
+
+
+def test_step_gating_options(golden_dir):
+    """generation_start_steps / guidance_start_steps / class_guidance_start_steps of sample() and tiled_sample()
+    (model.py:3196-3228, 3349-3356) against the unmodified reference (tests/golden/make_golden_options.py)."""
+    g = _load(golden_dir, "options_tiny")
+    spec = O.UnetSpec(dim=16)
+    sd = O.make_state_dict(spec, 11)
+    gen = torch.Generator().manual_seed(21)
+    cond01 = torch.rand(2, 3, 64, 64, generator=gen)
+    cond_t = torch.rand(1, 3, 272, 264, generator=gen)
+    assert abs(float(cond01.double().sum()) - float(g["cond01_checksum"])) < 1e-6
+    assert abs(float(cond_t.double().sum()) - float(g["cond_t_checksum"])) < 1e-6
+    torch.manual_seed(71)
+    a = O.sample(sd, spec, 2, cond01, class_label=torch.tensor([1]), class_cond_scale=2.5, class_guidance_start_steps=3,
+                 generation_start_steps=2, num_sample_steps=8, image_size=64)
+    torch.testing.assert_close(a, T(g["sample_a"]), rtol=0, atol=5e-4)
+    torch.manual_seed(71)
+    b = O.sample(sd, spec, 2, cond01, class_label=torch.tensor([0, 2]), cond_scale=1.7, guidance_start_steps=5,
+                 num_sample_steps=8, image_size=64)
+    torch.testing.assert_close(b, T(g["sample_b"]), rtol=0, atol=5e-4)
+    torch.manual_seed(71)
+    t = O.tiled_sample(sd, spec, 4, cond_t, torch.tensor([2]), class_cond_scale=2.0, class_guidance_start_steps=2,
+                       generation_start_steps=1, num_sample_steps=4)
+    torch.testing.assert_close(t[..., ::2, ::2], T(g["tiled_a_sub2"]), rtol=0, atol=5e-4)

@@ -188,3 +188,31 @@ def test_run_tiled_many_images_sharded_over_gloo():
     mp.spawn(_multi_worker, args=(2, _free_port(), ret2), nprocs=2, join=True)
     for r in range(2):
         assert torch.equal(ret2[r], single), f"rank {r} differs from the single-process run"
+
+
+def test_run_tiled_step_gating_options():
+    """generation_start_steps (start from q_sample(condition), skip the first steps) and class_guidance_start_steps
+    (scale 1 before that step) in the product loop == the oracle's tiled_sample (model.py:3305-3309, 3349-3360)."""
+    torch.set_num_threads(4)
+    sd = O.make_state_dict(SPEC, 11)
+    cond01, label = _inputs()
+    gen_start, cls_start = 1, 3
+    gen = torch.Generator().manual_seed(71)
+    cond = cond01 * 2 - 1
+    plan = TilePlan(cond.shape[2], cond.shape[3], TILE, TILE)
+    cond = F.pad(cond, plan.canvas_pad, mode="reflect")
+    # what ConditionalContinuousTimeGaussianDiffusionSR.tiled_sample does for generation_start_steps > 0
+    start = torch.tensor(1. - gen_start / STEPS)
+    img, _ = O.q_sample(cond, start, generator=gen)
+    it, ib, il, ir = plan.inner
+    cond_canvas = torch.zeros_like(cond)
+    cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
+    steps = torch.linspace(1., 0., STEPS + 1)
+    img, _ = run_tiled(TorchOps(sd, gen), img, cond_canvas, plan, steps, STEPS, BATCH, label, 1.0, 0, 2.0, cls_start,
+                       gen_start)
+    top, bottom, left, right = plan.crop
+    got = (img[:, :, top:bottom, left:right].clamp(-1, 1) + 1) * 0.5
+    ref = O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, class_guidance_start_steps=cls_start,
+                         generation_start_steps=gen_start, num_sample_steps=STEPS, tile_size=TILE, tile_stride=TILE,
+                         generator=torch.Generator().manual_seed(71))
+    assert torch.equal(got, ref)
