@@ -91,8 +91,15 @@ def sr_target_images(images, sr_model, scale=4, batch_size=8, test_label=2, cond
     return outs
 
 
-def sr_target_image(image, sr_model, **kw):
-    return sr_target_images([image], sr_model, **kw)[0]
+def sr_target_image(image, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
+                    class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
+                    num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71):
+    """Same name, arguments and defaults as the reference's per-image function (inference.py:59-98)."""
+    return sr_target_images([image], sr_model, scale=scale, batch_size=batch_size, test_label=test_label,
+                            cond_scale=cond_scale, guidance_start_steps=guidance_start_steps,
+                            class_cond_scale=class_cond_scale, class_guidance_start_steps=class_guidance_start_steps,
+                            generation_start_steps=generation_start_steps, num_sample_steps=num_sample_steps,
+                            enable_amp=enable_amp, interpolation=interpolation, seed=seed)[0]
 
 
 def try_open_image(image_path):

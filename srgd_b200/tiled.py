@@ -128,6 +128,11 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
             return ops.gather(canvas[lo:lo + 1], chunk, tile)
         return torch.cat([ops.gather(canvas[k:k + 1], chunk, tile) for k in range(lo, hi)], 0)
 
+    def scatter_all(canvas, coords, stack):                # stack: [n_img * len(coords), ...] image-major
+        n = len(coords)
+        for k in range(n_img):
+            ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
+
     for i in range(num_sample_steps):
         if i < generation_start_steps:
             continue
@@ -157,11 +162,6 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
             mine_out.append(outs[0] if len(outs) == 1 else torch.cat(outs, 0))
             mine_x0.append(x0s[0] if len(x0s) == 1 else torch.cat(x0s, 0))
             mine_idx.append(ci)
-
-        def scatter_all(canvas, coords, stack):
-            n = len(coords)
-            for k in range(n_img):
-                ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
 
         if world == 1:
             for ci, out, x0 in zip(mine_idx, mine_out, mine_x0):
