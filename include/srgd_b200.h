@@ -305,12 +305,6 @@ int srgd_profile_get(int kind, double* ms, double* flops, double* bytes, int* la
 int srgd_profile_record_count(void);
 int srgd_profile_record(int index, int* kind, double* ms, double* flops, double* bytes);
 
-/* Test-only probe (not on the product path): D[128][128] = W[128][64] * X[shift:shift+128][64]^T with the B-operand
- * descriptor's start address shifted by `shift` 128-byte rows inside a SWIZZLE_128B tile and base_offset field
- * `base_off` -- the mechanism behind the conv kernels' horizontal-tap halo reuse (tests/test_gpu_kernels.py). */
-int srgd_debug_umma_shift(const void* w, const void* x, float* out, int32_t shift, int32_t base_off,
-                          srgd_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -467,41 +467,39 @@ def get_area(coords, height, width):
     return coord, pad
 
 
-def tiled_sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale=1.0,
-                 guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
-                 generation_start_steps=0, num_sample_steps=250, tile_size=256, tile_stride=256,
-                 generator=None, clip=True):
-    """model.py:3288-3413 (start_white_noise=True path; RNG call order preserved)."""
+def tiled_setup(condition_x, tile_size=256, tile_stride=256):
+    """Canvas set-up of tiled_sample, model.py:3296-3342: reflect-padded condition in [-1,1], the two tile
+    grids, the hull of the shifted grid, the hull-masked condition canvas and the crop window."""
     condition_x = condition_x * 2 - 1
     batch, c, h, w = condition_x.shape
     (left, top, right, bottom), pad = get_coord_and_pad(h, w)       # model.py:3301 (default 256!)
     condition_x = F.pad(condition_x, pad, mode="reflect")
-    if generation_start_steps > 0:
-        st = 1. - torch.tensor(generation_start_steps / num_sample_steps, device=condition_x.device)
-        img, _ = q_sample(condition_x, st.reshape(1).expand(batch), generator=generator)
-    else:
-        img = torch.randn(condition_x.shape, generator=generator, device=condition_x.device)
-    steps = torch.linspace(1., 0., num_sample_steps + 1, device=condition_x.device)
     _, _, height, width = condition_x.shape
     coords0 = get_coords(height, width, tile_size, tile_size, 0)
     if height <= tile_size and width <= tile_size:
         coords1 = get_coords(height, width, tile_size, tile_stride, 0)
     else:
         coords1 = get_coords(height - tile_size, width - tile_size, tile_size, tile_stride, tile_size // 2)
-    coord_list = [coords0, coords1]
     (sleft, stop, sright, sbottom), small_pad = get_area(coords1, height, width)
-    condition_x = F.pad(condition_x[:, :, stop:sbottom, sleft:sright], small_pad, mode="constant", value=0)
-    x_start = img.clone()
-    for i in range(num_sample_steps):
-        if i < generation_start_steps:
-            continue
+    masked = F.pad(condition_x[:, :, stop:sbottom, sleft:sright], small_pad, mode="constant", value=0)
+    return dict(padded=condition_x, masked=masked, coord_list=[coords0, coords1],
+                hull=(stop, sbottom, sleft, sright), crop=(top, bottom, left, right))
+
+
+def tiled_steps(sd, spec, img, x_start, masked_condition, coord_list, hull, steps, first, last, batch_size,
+                class_label=None, cond_scale=1.0, guidance_start_steps=0, class_cond_scale=1.0,
+                class_guidance_start_steps=0, generator=None, clip=True):
+    """Steps [first, last) of the sampling loop of tiled_sample, model.py:3345-3401, on the canvas `img`
+    (updated in place where the reference does; the re-noised canvas is a new tensor, returned)."""
+    stop, sbottom, sleft, sright = hull
+    for i in range(first, last):
         cs = 1.0 if i < guidance_start_steps else cond_scale
         ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
         cur = coord_list[i % 2]
         for s0 in range(0, len(cur), batch_size):
             chunk = cur[s0:s0 + batch_size]
             mb = torch.cat([img[:, :, hs:he, ws:we] for hs, he, ws, we in chunk], 0)
-            mc = torch.cat([condition_x[:, :, hs:he, ws:we] for hs, he, ws, we in chunk], 0)
+            mc = torch.cat([masked_condition[:, :, hs:he, ws:we] for hs, he, ws, we in chunk], 0)
             out, x0 = p_sample(sd, spec, mb, steps[i], mc, class_label, cs, ccs, steps[i + 1],
                                generator=generator, clip=clip)
             for k, (hs, he, ws, we) in enumerate(chunk):
@@ -509,7 +507,29 @@ def tiled_sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale
                 x_start[:, :, hs:he, ws:we] = x0[k]
         if i % 2 == 1:
             cropped = img[:, :, stop:sbottom, sleft:sright]
-            img, _ = q_sample(torch.zeros_like(condition_x), steps[i + 1], generator=generator)
+            img, _ = q_sample(torch.zeros_like(masked_condition), steps[i + 1], generator=generator)
             img[:, :, stop:sbottom, sleft:sright] = cropped
+    return img, x_start
+
+
+def tiled_sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale=1.0,
+                 guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                 generation_start_steps=0, num_sample_steps=250, tile_size=256, tile_stride=256,
+                 generator=None, clip=True):
+    """model.py:3288-3413 (start_white_noise=True path; RNG call order preserved)."""
+    batch = condition_x.shape[0]
+    ts = tiled_setup(condition_x, tile_size, tile_stride)
+    padded = ts["padded"]
+    if generation_start_steps > 0:
+        st = 1. - torch.tensor(generation_start_steps / num_sample_steps, device=padded.device)
+        img, _ = q_sample(padded, st.reshape(1).expand(batch), generator=generator)
+    else:
+        img = torch.randn(padded.shape, generator=generator, device=padded.device)
+    steps = torch.linspace(1., 0., num_sample_steps + 1, device=padded.device)
+    x_start = img.clone()
+    img, _ = tiled_steps(sd, spec, img, x_start, ts["masked"], ts["coord_list"], ts["hull"], steps,
+                         max(0, generation_start_steps), num_sample_steps, batch_size, class_label, cond_scale,
+                         guidance_start_steps, class_cond_scale, class_guidance_start_steps, generator, clip)
+    top, bottom, left, right = ts["crop"]
     img = img[:, :, top:bottom, left:right].clamp(-1., 1.)
     return (img + 1) * 0.5

@@ -110,7 +110,6 @@ SIGNATURES = {
     "srgd_profile_end": (C.c_int, []),
     "srgd_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int)]),
-    "srgd_debug_umma_shift": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "srgd_profile_record_count": (C.c_int, []),
     "srgd_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),

@@ -107,3 +107,51 @@ def unet_keys(spec: UnetSpec) -> Dict[str, Tuple[int, ...]]:
     k["final_conv.weight"] = (spec.channels, spec.dim, 1, 1)
     k["final_conv.bias"] = (spec.channels,)
     return k
+
+
+def seeded_state_dict(spec: UnetSpec, seed: int = 1234, prefix: str = "model.", init: str = "unit"):
+    """Deterministic random-init checkpoint contents `{prefix + key: fp32 tensor}` of the reference architecture, for
+    benchmarks and smoke runs when the shipped .pth is only a Git-LFS pointer.
+
+    init="torch": the distributions the reference constructors produce (nn.Conv2d / nn.Linear defaults U(+-1/sqrt(fan_in))
+    for weight and bias, norm gains 1 / biases 0, nn.Embedding and the sinusoidal frequencies N(0,1), the pixel-shuffle
+    conv = kaiming-uniform rows repeated x4 with zero bias, model.py:88-95).
+    init="unit": a harsher stress init (unit-gain weights, jittered norm gains, non-zero biases) that exercises every
+    gain / bias path with O(1..3) activations; this is what bench.py loads.
+    Draw order = checkpoint key order, so the tensors equal the ones the parity tests load, bit for bit
+    (tests/test_host_logic.py checks that)."""
+    import math
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    keys = unet_keys(spec)
+    sd = {}
+    for name, shape in keys.items():
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        if name.endswith("time_mlp.0.weights") or name.endswith("class_mlp.0.weight"):
+            t = torch.randn(shape, generator=g)
+        elif name.endswith(".g") or name.endswith("norm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g) if init == "unit" else torch.ones(shape)
+        elif name.endswith("norm.bias"):
+            t = 0.1 * torch.randn(shape, generator=g) if init == "unit" else torch.zeros(shape)
+        elif name.endswith(".bias"):
+            if init == "unit":
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+            elif ".net.0." in name:
+                t = torch.zeros(shape)
+            else:
+                fi = 1
+                for s in keys[name[:-4] + "weight"][1:]:
+                    fi *= s
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fi)
+        elif init == "torch" and ".net.0.weight" in name:
+            o, i, kh, kw = shape
+            base = (torch.rand((o // 4, i, kh, kw), generator=g) * 2 - 1) * math.sqrt(6.0 / (i * kh * kw))
+            t = base.repeat_interleave(4, dim=0)
+        else:
+            bound = math.sqrt(3.0 / fan_in) if init == "unit" else 1.0 / math.sqrt(fan_in)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        sd[prefix + name] = t.float().contiguous()
+    return sd

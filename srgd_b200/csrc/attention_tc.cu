@@ -266,10 +266,9 @@ extern "C" int srgd_attention_tc(const void* qkv, void* out, int32_t B, int32_t 
   kp.N = N;
   kp.heads = heads;
   kp.scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaTcSmem::kTotal));
-    configured = true;
   }
   cudaStream_t st = as_stream(stream);
   ProfScope prof(SRGD_PK_FULL_ATTN, 4.0 * (double)B * heads * (double)N * N * 32, 2.0 * (double)B * N * heads * 32 * 4, st);

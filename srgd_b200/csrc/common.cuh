@@ -42,6 +42,18 @@ int fail_cuda(cudaError_t e, const char* what);
 static inline cudaStream_t as_stream(srgd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute and the library may be used on
+// several GPUs from one process (srgd_device_check / ConditionalSRUnet.to(device)): a launcher keeps one bit per
+// device index in a static mask and (re)configures its kernel on the first launch on each device.
+static inline bool first_launch_on_device(uint64_t& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // launch counter (gpu_launches in bench.py / srgd_unet_last_launch_count)
 extern thread_local long g_launches;
 static inline void count_launch(int n = 1) { g_launches += n; }

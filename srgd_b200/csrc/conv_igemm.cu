@@ -839,11 +839,10 @@ static int validate_desc(const srgd_conv_desc* d) {
 template <int BN, int STAGES>
 static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
   using L = ConvSmem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::kTotal));
-    configured = true;
   }
   int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
   SRGD_CUDA_OK(launch_k(conv_igemm_kernel<BN, STAGES>, dim3(grid), dim3(kThreads), L::kTotal, st, kp));
@@ -854,10 +853,9 @@ static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
 template <bool HALO>
 static int launch_igemm_t(const ConvKernelParams& kp, cudaStream_t st) {
   using L = ConvSmemT<HALO>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_t_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
   SRGD_CUDA_OK(launch_k(conv_igemm_t_kernel<HALO>, dim3(grid), dim3(kThreads), L::kTotal, st, kp));

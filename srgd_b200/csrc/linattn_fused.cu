@@ -590,10 +590,9 @@ static int la_splits_for(int B, int tiles_per_sample) {
 template <int C>
 static int launch_la_out(const LaOutParams& kp, int chunks, int B, cudaStream_t st) {
   using L = LaOutSmem<C>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   SRGD_CUDA_OK(launch_k(la_out_kernel<C>, dim3(chunks, B), dim3(320), L::kTotal, st, kp));
   SRGD_LAUNCH_OK("la_out_kernel");
@@ -663,10 +662,9 @@ extern "C" int srgd_linear_attention_block(const void* x, const float* inv_norm,
   rc = make_tmap_2d_bf16(&ap.w_map, qkv_w, C, 384, (uint64_t)C * 2, 64, 128, "linear_attention_block(qkv_w)");
   if (rc) return rc;
   ap.inv = inv; ap.part = part; ap.C = C; ap.splits = splits; ap.tiles_per_sample = tiles;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaCtxSmem::kTotal));
-    configured = true;
   }
   SRGD_CUDA_OK(launch_k(la_ctx_kernel, dim3(splits, B), dim3(320), LaCtxSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_kernel");

@@ -636,11 +636,10 @@ int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, cons
   rc = make_tmap_2d_bf16(&ap.w_map, qkv_w, 128, 384, 256, 64, 128, "linear_attention_block(qkv_w)");
   if (rc) return rc;
   ap.inv = inv; ap.part = part; ap.splits = splits; ap.tiles_per_sample = tiles;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_ctx_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaCtxPpSmem::kTotal));
     SRGD_CUDA_OK(cudaFuncSetAttribute(la_out_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LaOutPpSmem::kTotal));
-    configured = true;
   }
   SRGD_CUDA_OK(launch_k(la_ctx_pp_kernel, dim3(splits, B), dim3(576), LaCtxPpSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_pp_kernel");

@@ -243,8 +243,8 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
         batch = shape[0]
         dev = self.device
         if generation_start_steps > 0:
-            start = 1. - generation_start_steps / num_sample_steps
-            img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32))
+            start = 1. - torch.tensor(generation_start_steps / num_sample_steps)       # fp32, model.py:3199
+            img, _ = self.q_sample(condition_x, start)
         else:
             img = self._randn(shape, dev)                                       # RNG draw #0 (model.py:3203)
         images = [img.clone().cpu()] if with_images else None
@@ -302,9 +302,8 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
             return noise if batch == 1 else noise.expand(batch, -1, -1, -1).contiguous()
 
         if generation_start_steps > 0:
-            start = 1. - generation_start_steps / num_sample_steps
-            img, _ = self.q_sample(condition_x, torch.tensor(start, dtype=torch.float32),
-                                   noise=shared(self._randn(one, self.device)))
+            start = 1. - torch.tensor(generation_start_steps / num_sample_steps)       # fp32, model.py:3306
+            img, _ = self.q_sample(condition_x, start, noise=shared(self._randn(one, self.device)))
         elif start_white_noise:
             img = shared(self._randn(one, self.device))                         # RNG draw #0 (model.py:3311)
         else:
@@ -324,10 +323,10 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
 
         def on_step(i, cur, cur_x0):
             next(bar_it, None)                                                  # progress bar tick
-            if with_images:
-                images.append(cur[:, :, top:bottom, left:right].clone().cpu())
-            if with_x0_images:
-                x0_images.append(cur_x0[:, :, top:bottom, left:right].clone().cpu())
+            if with_images:                                                     # the reference keeps the
+                images.append(cur.clone().cpu())                                # UNCROPPED canvas for every step
+            if with_x0_images:                                                  # after the first frame
+                x0_images.append(cur_x0.clone().cpu())                          # (model.py:3398-3401)
 
         from .tiled import CudaTiledOps, run_tiled
         img = img.contiguous()

@@ -90,11 +90,15 @@ class ConditionalSRUnet(nn.Module):
         self._handle = None
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
+        # A load through a PARENT module (`diffusion.load_state_dict(ckpt['ema_model'])`, the documented path) never
+        # calls this module's load_state_dict, only its _load_from_state_dict + post hooks: drop the packed device
+        # weights there too.  In-place edits of a parameter are caught by the version key in _ensure_handle.
+        self.register_load_state_dict_post_hook(ConditionalSRUnet._after_load)
         self._workspaces: Dict[Tuple[int, int, int], torch.Tensor] = {}
         self.conv_impl = 0          # debug knob: 1 = CUDA-core direct conv, 2 = stand-alone GN statistics
         self.last_launches = 0
 
-    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspaces")
+    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspaces", "_plist", "_labels_ok")
 
     def __deepcopy__(self, memo):
         # device handles / packed weights are per-instance runtime state: a copy re-packs lazily
@@ -116,12 +120,17 @@ class ConditionalSRUnet(nn.Module):
         self._drop_handle()
         return r
 
+    @staticmethod
+    def _after_load(module, incompatible_keys) -> None:
+        module._drop_handle()
+
     def _drop_handle(self):
         if getattr(self, "_handle", None) is not None:
             _lib.load().srgd_unet_destroy(self._handle)
         self._handle = None
         self._packed = None
         self._workspaces = {}
+        self.__dict__["_plist"] = None
 
     def __del__(self):
         try:
@@ -129,9 +138,26 @@ class ConditionalSRUnet(nn.Module):
         except Exception:
             pass
 
+    def _weights_key(self, device):
+        """(device, sum of the parameters' in-place version counters): any optimizer-style or manual in-place
+        change of a weight bumps its `_version`, so a stale pack is never reused."""
+        v = 0
+        plist = self.__dict__.get("_plist")
+        if plist is None:                  # flat parameter list (walking the module tree costs ~0.7 ms per call)
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        try:
+            for p in plist:
+                v += p._version
+        except RuntimeError:               # inference tensors carry no version counter (and cannot be edited in place)
+            v = -1
+        return (device, v)
+
     def _ensure_handle(self, device: torch.device):
-        if self._handle is not None and self._packed_key == device:
+        key = self._weights_key(device)
+        if self._handle is not None and self._packed_key == key:
             return
+        if self._handle is not None:
+            self._drop_handle()
         lib = _lib.load()
         _lib.check(lib.srgd_device_check(device.index if device.index is not None else torch.cuda.current_device()),
                    "srgd_device_check")
@@ -146,7 +172,7 @@ class ConditionalSRUnet(nn.Module):
             cfg = weights.make_config(self.spec)
             handle = C.c_void_p()
             _lib.check(lib.srgd_unet_create(C.byref(cfg), arr, len(names), C.byref(handle)), "srgd_unet_create")
-        self._handle, self._packed, self._packed_key = handle, packed, device
+        self._handle, self._packed, self._packed_key = handle, packed, key
         self._workspaces = {}
 
     def _workspace(self, B: int, H: int, W: int, device) -> torch.Tensor:
@@ -195,12 +221,32 @@ class ConditionalSRUnet(nn.Module):
         """int32 device labels for `rows` rows from the reference-style class_label ([B] or [1] int64)."""
         if class_label is None or self.num_classes is None:
             return None
-        lab = class_label.to(device=device).reshape(-1).to(torch.int32)
+        lab = class_label.reshape(-1)
+        # nn.Embedding raises IndexError for an out-of-range label (model.py:612, 693); negative values are reserved
+        # for the internally generated null rows of the guidance batch and never come from a caller
+        self._check_labels(lab)
+        lab = lab.to(device=device).to(torch.int32)
         if lab.numel() == 1 and rows != 1:
             lab = lab.expand(rows)
         if lab.numel() != rows:
             raise RuntimeError(f"class_label has {lab.numel()} entries for a batch of {rows}")
         return lab.contiguous()
+
+    def _check_labels(self, lab: torch.Tensor) -> None:
+        """Host labels are validated on every call; a device label costs one sync, so it is validated once per
+        distinct tensor (same storage, same version) -- sampling loops pass the same label tensor every step."""
+        key = None
+        if lab.is_cuda:
+            try:
+                ver = lab._version
+            except RuntimeError:           # created under inference_mode: immutable
+                ver = -1
+            key = (lab.data_ptr(), ver, lab.numel(), lab.device.index)
+            if key == getattr(self, "_labels_ok", None):
+                return
+        if lab.numel() and (int(lab.min()) < 0 or int(lab.max()) >= self.num_classes):
+            raise IndexError(f"class_label {lab.tolist()[:8]} out of range for num_classes={self.num_classes}")
+        self._labels_ok = key
 
     def forward(self, x, time, class_label=None, x_self_cond=None):
         assert all(d % self.downsample_factor == 0 for d in x.shape[-2:]), \

@@ -1,4 +1,4 @@
-// Micro-experiment (test-only entry point, not on the product path): does tcgen05.mma accept a K-major
+// Micro-experiment (test-only probe library built by tests/gpu_probe_umma_shift.py; NOT part of libsrgd_b200.so): does tcgen05.mma accept a K-major
 // SWIZZLE_128B operand whose start address is shifted by whole 128-byte rows (not 1024-byte aligned), and which
 // value of the descriptor's base_offset field (bits [49,52)) does it need?  A 3x3 convolution could then take its
 // three horizontal taps from ONE shared-memory copy of an image-row segment (halo reuse) instead of three TMA loads.
@@ -6,9 +6,9 @@
 #include <cuda.h>
 #include <string.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
-#include "tmap.h"
+#include "../../srgd_b200/csrc/common.cuh"
+#include "../../srgd_b200/csrc/ptx.cuh"
+#include "../../srgd_b200/csrc/tmap.h"
 
 namespace srgd {
 

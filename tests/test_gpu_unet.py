@@ -251,3 +251,23 @@ def test_launch_count_reported():
     x = torch.randn(1, 3, 64, 64, device="cuda")
     diff.model(x, torch.zeros(1, device="cuda"), None, None)
     assert diff.model.last_launches > 100
+
+
+def test_reload_through_the_diffusion_wrapper_repacks_the_device_weights():
+    """a model that has already run on the GPU and then receives new weights through the
+    documented `ema_model.module.load_state_dict(ckpt['ema_model'])` path must sample with the NEW weights."""
+    spec = O.UnetSpec(dim=64)
+    sd_a, sd_b = O.make_state_dict(spec, 22), O.make_state_dict(spec, 23)
+    diff = make_diffusion(spec, sd_a, 64, 250)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 64, 64, generator=g).cuda()
+    lsnr = torch.tensor([0.3, -1.0]).cuda()
+    a = diff.model(x, lsnr, None, None)
+    diff.load_state_dict({k: v.cuda() for k, v in sd_b.items()}, strict=True)       # nested load, model already on GPU
+    b = diff.model(x, lsnr, None, None)
+    fresh = make_diffusion(spec, sd_b, 64, 250).model(x, lsnr, None, None)
+    assert torch.equal(b, fresh) and not torch.equal(a, b)
+    with torch.no_grad():                                                           # in-place edit of one parameter
+        diff.model.final_conv.bias.add_(0.5)
+    c = diff.model(x, lsnr, None, None)
+    assert float((c - b - 0.5).abs().max()) < 1e-5

@@ -202,3 +202,41 @@ def test_inference_directory_loop_groups_equal_sizes(tmp_path, capsys):
     assert Stub.calls == [(2, 3, 32, 40), (1, 3, 32, 40), (1, 3, 32, 48)]
     assert sorted(os.listdir(out_dir)) == ["a_out.png", "b_out.png", "c_out.png", "d_out.png", "e_out.png"]
     assert Image.open(out_dir / "d_out.png").size == (48, 32)
+
+
+def test_nested_load_and_inplace_edit_invalidate_packed_weights():
+    """`diffusion.load_state_dict(ckpt['ema_model'])` -- the documented path -- reaches the U-Net
+    only through _load_from_state_dict, never through its load_state_dict override; the packed device weights must
+    still be dropped, and an in-place edit of any parameter must change the pack key."""
+    import model as M
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=64)
+    drops = []
+    orig = unet._drop_handle
+    unet._drop_handle = lambda: (drops.append(1), orig())[1]
+    diff.load_state_dict(diff.state_dict(), strict=True)
+    assert len(drops) == 1
+    k0 = unet._weights_key("dev")
+    with torch.no_grad():
+        unet.final_conv.bias.add_(1.0)
+    assert unet._weights_key("dev") != k0
+
+
+def test_out_of_range_class_label_raises_like_nn_embedding():
+    """the reference's nn.Embedding raises IndexError for label >= num_classes (model.py:612, 693)."""
+    import model as M
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    assert unet.labels_for(torch.tensor([2]), 4, "cpu").tolist() == [2, 2, 2, 2]
+    for bad in (3, -1):
+        with pytest.raises(IndexError):
+            unet.labels_for(torch.tensor([bad]), 1, "cpu")
+
+
+@pytest.mark.parametrize("init", ["unit", "torch"])
+def test_seeded_state_dict_equals_the_oracles(init):
+    """bench.py / smoke load `arch.seeded_state_dict` (product side, no oracle import); the parity tests load the
+    oracle's `make_state_dict`: the two must be the same tensors so that parity is shown on the benchmarked weights."""
+    spec_p, spec_o = arch.UnetSpec(dim=64), O.UnetSpec(dim=64)
+    a, b = arch.seeded_state_dict(spec_p, 1234, init=init), O.make_state_dict(spec_o, 1234, init=init)
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
