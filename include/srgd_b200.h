@@ -296,6 +296,13 @@ enum {
   SRGD_PK_OTHER = 6,       /* pack_input, final_conv, embeddings, q_sample…  */
   SRGD_PK_COUNT = 7
 };
+/* Batch-invariant reductions (returns the previous setting).  The only reduction of the path whose partition depends
+ * on the launch's batch size is the LinearAttention context k.softmax(N) v^T (model.py:317-320): its per-sample partials
+ * are split over SMs / B thread blocks.  With `on` != 0 the split of a fixed reference batch is used instead, so a row's
+ * result no longer depends on which other rows share its launch: tile-sharded sampling (tiled_sample(shard_tiles=True))
+ * then yields a bit-identical image for every world size and call partition.  Process-wide; default off. */
+int srgd_set_batch_invariant(int on);
+
 int srgd_profile_begin(void);
 int srgd_profile_end(void);
 /* Sums since srgd_profile_begin for one kind: device milliseconds, algorithmic FLOPs and bytes the

@@ -25,6 +25,7 @@ int fail_cuda(cudaError_t e, const char* what) {
 }
 
 static int g_sm_count = 0;
+int g_batch_invariant = 0;
 
 int check_device() {
   static thread_local int cached_dev = -1;
@@ -114,6 +115,12 @@ int srgd_device_check(int device) {
   int rc = srgd::check_device();
   cudaSetDevice(cur);
   return rc;
+}
+
+int srgd_set_batch_invariant(int on) {
+  const int prev = srgd::g_batch_invariant;
+  srgd::g_batch_invariant = on ? 1 : 0;
+  return prev;
 }
 
 int srgd_profile_begin(void) {

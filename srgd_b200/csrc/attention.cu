@@ -249,13 +249,19 @@ __global__ void __launch_bounds__(kFaQ) full_attention_kernel(const bf16* __rest
   }
 }
 
-static int la_splits(int B, int N) {
+static int la_splits_mode(int B, int N, bool invariant) {
+  if (invariant) B = kInvariantRefBatch;                 // partition independent of the launch's batch size
   int s = (4 * sm_count() + B - 1) / B;                  // ~4 blocks per SM overall
   int max_s = (N + 2 * kLaTile - 1) / (2 * kLaTile);     // at least two tiles per block
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 1024) s = 1024;
   return s;
+}
+static int la_splits(int B, int N) { return la_splits_mode(B, N, g_batch_invariant != 0); }
+static int la_splits_max(int B, int N) {
+  const int a = la_splits_mode(B, N, false), b = la_splits_mode(B, N, true);
+  return a > b ? a : b;
 }
 
 }  // namespace srgd
@@ -264,7 +270,7 @@ using namespace srgd;
 
 extern "C" size_t srgd_linear_attention_workspace(int32_t B, int32_t N, int32_t heads) {
   if (B <= 0 || N <= 0 || heads <= 0) return 0;
-  const size_t part = (size_t)B * la_splits(B, N) * heads * kDH * 34 * sizeof(float);
+  const size_t part = (size_t)B * la_splits_max(B, N) * heads * kDH * 34 * sizeof(float);
   const size_t ctx = (size_t)B * heads * kDH * kDH * sizeof(float);
   return part + ctx + 256;
 }

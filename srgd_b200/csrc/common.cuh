@@ -54,6 +54,12 @@ static inline bool first_launch_on_device(uint64_t& mask) {
   return true;
 }
 
+// srgd_set_batch_invariant(): when non-zero, every reduction whose partition would otherwise depend on the batch size
+// (the LinearAttention context partials: splits per sample = SMs / B) uses the partition of a fixed reference batch,
+// so a row's result is bit-identical no matter which other rows share its launch.
+extern int g_batch_invariant;
+constexpr int kInvariantRefBatch = 16;
+
 // launch counter (gpu_launches in bench.py / srgd_unet_last_launch_count)
 extern thread_local long g_launches;
 static inline void count_launch(int n = 1) { g_launches += n; }

@@ -580,11 +580,17 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
 int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, const float* out_b, const float* out_g,
                        void* out, int B, int N, const float* inv, float* part, bf16* bd, int splits, cudaStream_t st);
 
-static int la_splits_for(int B, int tiles_per_sample) {
-  int s = sm_count() / B;
+static int la_splits_mode(int B, int tiles_per_sample, bool invariant) {
+  int s = sm_count() / (invariant ? kInvariantRefBatch : B);
   if (s < 1) s = 1;
   if (s > tiles_per_sample) s = tiles_per_sample;
   return s;
+}
+static int la_splits_for(int B, int tiles_per_sample) { return la_splits_mode(B, tiles_per_sample, g_batch_invariant != 0); }
+// workspace sizing covers both modes: the flag may change between srgd_unet_workspace_bytes and the forward
+static int la_splits_max(int B, int tiles_per_sample) {
+  const int a = la_splits_mode(B, tiles_per_sample, false), b = la_splits_mode(B, tiles_per_sample, true);
+  return a > b ? a : b;
 }
 
 template <int C>
@@ -610,7 +616,7 @@ extern "C" int srgd_linear_attention_block_supported(int32_t N, int32_t C, int32
 
 extern "C" size_t srgd_linear_attention_block_workspace(int32_t B, int32_t N, int32_t C, int32_t heads) {
   if (!srgd_linear_attention_block_supported(N, C, heads) || B <= 0) return 0;
-  const int splits = la_splits_for(B, N / 128);
+  const int splits = la_splits_max(B, N / 128);
   // C = 128 runs two pipelines per CTA (linattn_pp.cu): two partial records per split
   return (size_t)B * N * sizeof(float) + (size_t)B * 2 * splits * kLfHid * 34 * sizeof(float) +
          (size_t)B * C * kLfHid * 2 + 1024;

@@ -10,11 +10,16 @@ every 256x256 tile of the current grid -- the aligned grid on even steps, the gr
 steps -- in minibatches of `batch_size` tiles; after odd steps everything outside the hull of the shifted grid is
 replaced by fresh noise at the next noise level.
 
-Multi-GPU ("exact mode"): tiles of one step are independent, but step i+1's grid straddles
-step i's tiles, so every rank keeps a full replica of the canvas, denoises the minibatches assigned to it
-(round-robin over the reference's minibatch order) and the freshly written tiles are all-gathered once per step.
-RNG parity: every rank draws the noise of ALL minibatches in the reference's order (same generator state on every
-rank) and uses only its own, so the result is bit-identical to the single-process run for any world size.
+Multi-GPU ("exact mode", SURVEY.md section 8e, `shard=True`): tiles of one step are independent, but step i+1's
+grid straddles step i's tiles, so every rank keeps a full replica of the canvas, denoises a CONTIGUOUS RANGE OF
+TILES of the step's grid (row bands; balanced to within one tile for any world size and independent of the
+reference's `batch_size`), and the freshly written tiles travel in ONE pre-sized `all_gather_into_tensor` per step,
+issued asynchronously so that the odd steps' full-canvas noise draw overlaps it.
+RNG parity: every rank draws the noise of ALL minibatches in the reference's order and shapes (same generator state
+on every rank) and uses the rows of its own tiles.  Denoiser calls are regrouped (up to `max_rows` rows per call
+instead of `batch_size`), which is only legitimate because the library runs in batch-invariant mode there
+(`srgd_set_batch_invariant`: a tile's result does not depend on which other tiles share its launch) -- the image is
+then bit-identical for every world size, 1 included.
 """
 from __future__ import annotations
 
@@ -24,6 +29,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
+from .sharding import shard_range
 from .tiling import TilePlan
 
 
@@ -86,20 +92,41 @@ class CudaTiledOps:
     def finalize(self, img):
         return self.d._finalize(img)
 
+    def set_batch_invariant(self, on: bool) -> bool:
+        """Returns the previous setting (include/srgd_b200.h: srgd_set_batch_invariant)."""
+        return bool(self._lib.load().srgd_set_batch_invariant(1 if on else 0))
+
 
 def _chunks(tiles: List[Tuple[int, int]], batch_size: int) -> List[List[Tuple[int, int]]]:
     return [tiles[i:i + batch_size] for i in range(0, len(tiles), batch_size)]
 
 
-def _all_gather_tiles(local: Optional[torch.Tensor], counts: List[int], shape_tail, device, dtype, group):
-    """All-gather per-rank tile stacks of different lengths (padded to the largest)."""
-    width = max(counts)
-    buf = torch.zeros((width,) + tuple(shape_tail), device=device, dtype=dtype)
-    if local is not None and local.shape[0] > 0:
-        buf[:local.shape[0]] = local
-    outs = [torch.empty_like(buf) for _ in counts]
-    dist.all_gather(outs, buf, group=group)
-    return [o[:c] for o, c in zip(outs, counts)]
+def _rows_of(noises: List[torch.Tensor], batch_size: int, lo: int, hi: int) -> torch.Tensor:
+    """Rows [lo, hi) of the per-minibatch noise draws `noises` (minibatch k holds tiles [k * batch_size, ...))."""
+    parts = []
+    t = lo
+    while t < hi:
+        k, off = divmod(t, batch_size)
+        take = min(hi - t, noises[k].shape[0] - off)
+        parts.append(noises[k][off:off + take])
+        t += take
+    return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+
+
+class _Exchange:
+    """Pre-sized send / receive buffers of one tile grid: send [n_img, width, C, T, T], recv [world, n_img, width, ...]
+    where width = the largest per-rank tile count; one all_gather_into_tensor per step fills `recv`."""
+
+    def __init__(self, n_tiles, n_img, world, tail, device, dtype, want_x0):
+        self.ranges = [shard_range(n_tiles, world, r) for r in range(world)]
+        width = max(1, max(hi - lo for lo, hi in self.ranges))
+        shape = (n_img, width) + tuple(tail)
+        self.send = torch.zeros(shape, device=device, dtype=dtype)
+        self.recv = torch.empty((world,) + shape, device=device, dtype=dtype) if world > 1 else self.send[None]
+        self.send_x0 = torch.zeros(shape, device=device, dtype=dtype) if want_x0 else None
+        self.recv_x0 = None
+        if want_x0:
+            self.recv_x0 = torch.empty((world,) + shape, device=device, dtype=dtype) if world > 1 else self.send_x0[None]
 
 
 def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan, steps: torch.Tensor,
@@ -108,19 +135,24 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
               x_start: Optional[torch.Tensor] = None, on_step=None, group=None, shard: bool = False,
               max_rows: int = 64):
     """The sampling loop of tiled_sample (model.py:3345-3401) on an initial noise canvas `img` [N,3,H,W] and the
-    hull-masked condition canvas.  Updates and returns `img` (and `x_start` if given).  With `shard=True` and an
-    initialised process group the minibatches of every step are split over the ranks (see module docstring).
+    hull-masked condition canvas.  Updates and returns `img` (and `x_start` if given).
+
+    shard=False: the reference's own partition -- one denoiser call per minibatch of `batch_size` tiles.
+    shard=True : tile-granular exact mode (module docstring): contiguous tile ranges per rank of the initialised
+    process group (or the whole grid without one), calls of up to `max_rows` rows, batch-invariant kernels, one
+    all-gather per step.
 
     N > 1 (extension; the reference's loop only works for N = 1): N images of the same size advance together and
     SHARE the noise stream, which is exactly what N consecutive runs of the reference CLI produce -- it reseeds every
-    generator before each image (inference.py:81).  The tiles of a minibatch are stacked image-major into one
-    denoiser batch of at most `max_rows` rows, so the 4-tile odd steps of a small image still fill the GPU."""
+    generator before each image (inference.py:81).  The tiles of a call are stacked image-major into one denoiser
+    batch of at most `max_rows` rows, so the 4-tile odd steps of a small image still fill the GPU."""
     tile = plan.tile_size
     world = dist.get_world_size(group) if (shard and dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     dev = img.device
     n_img = img.shape[0]
-    # the condition tiles of the two grids never change: gather them once per minibatch
+    tail = (img.shape[1], tile, tile)
+    # the condition tiles of the two grids never change: gather them once per denoiser call slot
     cond_cache = {}
 
     def gather_all(canvas, chunk, lo, hi):
@@ -133,66 +165,95 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
         for k in range(n_img):
             ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
 
-    for i in range(num_sample_steps):
-        if i < generation_start_steps:
-            continue
-        cs = 1.0 if i < guidance_start_steps else cond_scale
-        ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
-        last = float(steps[i + 1]) == 0.0
-        chunks = _chunks(plan.grids[i % 2], batch_size)
-        mine_out, mine_x0, mine_idx = [], [], []
-        for ci, chunk in enumerate(chunks):
-            # RNG: one draw per minibatch in the reference's order on EVERY rank (model.py:3187), none on the last step
-            noise = None if last else ops.randn((len(chunk), img.shape[1], tile, tile), dev)
-            if ci % world != rank:
-                continue
-            per_call = max(1, max_rows // len(chunk))          # images per denoiser call
-            outs, x0s = [], []
-            for lo in range(0, n_img, per_call):
-                hi = min(n_img, lo + per_call)
-                key = (i % 2, ci, lo)
-                if key not in cond_cache:
-                    cond_cache[key] = gather_all(cond_canvas, chunk, lo, hi)
-                xt = gather_all(img, chunk, lo, hi)
-                nz = noise if (noise is None or hi - lo == 1) else noise.repeat(hi - lo, 1, 1, 1)
-                out, x0 = ops.p_sample(xt, steps[i], cond_cache[key], class_label, cs, ccs, steps[i + 1], nz)
-                outs.append(out)
-                x0s.append(x0)
-            # [n_img * len(chunk), ...] image-major
-            mine_out.append(outs[0] if len(outs) == 1 else torch.cat(outs, 0))
-            mine_x0.append(x0s[0] if len(x0s) == 1 else torch.cat(x0s, 0))
-            mine_idx.append(ci)
+    def denoise(i, parity, slot, chunk, noise, cs, ccs, emit):
+        """One group of tiles `chunk` for all images, in calls of at most max_rows rows; emit(lo, hi, out, x0) receives
+        the image-major results of images [lo, hi)."""
+        per_call = max(1, max_rows // len(chunk))          # images per denoiser call
+        for lo in range(0, n_img, per_call):
+            hi = min(n_img, lo + per_call)
+            key = (parity, slot, lo)
+            if key not in cond_cache:
+                cond_cache[key] = gather_all(cond_canvas, chunk, lo, hi)
+            xt = gather_all(img, chunk, lo, hi)
+            nz = noise if (noise is None or hi - lo == 1) else noise.repeat(hi - lo, 1, 1, 1)
+            out, x0 = ops.p_sample(xt, steps[i], cond_cache[key], class_label, cs, ccs, steps[i + 1], nz)
+            emit(lo, hi, out, x0)
 
-        if world == 1:
-            for ci, out, x0 in zip(mine_idx, mine_out, mine_x0):
-                scatter_all(img, chunks[ci], out)
-                if x_start is not None:
-                    scatter_all(x_start, chunks[ci], x0)
-        else:
-            # exchange step: every rank contributes the tiles it wrote; all replicas apply all of them
-            counts = [n_img * sum(len(chunks[ci]) for ci in range(r, len(chunks), world)) for r in range(world)]
-            tail = (img.shape[1], tile, tile)
-            local = torch.cat(mine_out, 0) if mine_out else None
-            gathered = _all_gather_tiles(local, counts, tail, dev, img.dtype, group)
-            gathered_x0 = None
-            if x_start is not None:
-                local0 = torch.cat(mine_x0, 0) if mine_x0 else None
-                gathered_x0 = _all_gather_tiles(local0, counts, tail, dev, img.dtype, group)
-            for r in range(world):
-                pos = 0
-                for ci in range(r, len(chunks), world):
-                    n = n_img * len(chunks[ci])
-                    scatter_all(img, chunks[ci], gathered[r][pos:pos + n])
-                    if gathered_x0 is not None:
-                        scatter_all(x_start, chunks[ci], gathered_x0[r][pos:pos + n])
-                    pos += n
-        if i % 2 == 1:
-            # outside the hull of the shifted grid the state is replaced by fresh noise at the next noise level
-            # (q_sample of zeros, model.py:3392-3396); the draw covers the whole canvas like the reference's
-            fresh = ops.randn((1,) + tuple(img.shape[1:]), dev)
-            sig = ops.sigma(steps[i + 1])
-            for k in range(n_img):
-                ops.renoise_outside(img[k:k + 1], fresh, sig, plan.inner)
-        if on_step is not None:
-            on_step(i, img, x_start)
+    exchanges = {}
+    prev_invariant = None
+    if shard and hasattr(ops, "set_batch_invariant"):
+        prev_invariant = ops.set_batch_invariant(True)
+    try:
+        for i in range(num_sample_steps):
+            if i < generation_start_steps:
+                continue
+            cs = 1.0 if i < guidance_start_steps else cond_scale
+            ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
+            last = float(steps[i + 1]) == 0.0
+            parity = i % 2
+            tiles = plan.grids[parity]
+            chunks = _chunks(tiles, batch_size)
+            fresh = None
+            if not shard:
+                outs = []
+                for ci, chunk in enumerate(chunks):
+                    # RNG: one draw per minibatch in the reference's order (model.py:3187), none on the last step
+                    noise = None if last else ops.randn((len(chunk),) + tail, dev)
+                    got = []
+                    denoise(i, parity, ci, chunk, noise, cs, ccs, lambda lo, hi, out, x0: got.append((out, x0)))
+                    # [n_img * len(chunk), ...] image-major
+                    outs.append((chunk, got[0][0] if len(got) == 1 else torch.cat([g[0] for g in got], 0),
+                                 got[0][1] if len(got) == 1 else torch.cat([g[1] for g in got], 0)))
+                for chunk, out, x0 in outs:
+                    scatter_all(img, chunk, out)
+                    if x_start is not None:
+                        scatter_all(x_start, chunk, x0)
+            else:
+                ex = exchanges.get(parity)
+                if ex is None:
+                    ex = exchanges[parity] = _Exchange(len(tiles), n_img, world, tail, dev, img.dtype,
+                                                       x_start is not None)
+                # RNG: every rank draws the noise of ALL minibatches, same shapes and order as the reference
+                noises = None if last else [ops.randn((len(chunk),) + tail, dev) for chunk in chunks]
+                lo_t, hi_t = ex.ranges[rank]
+                for a in range(lo_t, hi_t, max_rows):
+                    sub = tiles[a:min(hi_t, a + max_rows)]
+                    nz = None if last else _rows_of(noises, batch_size, a, a + len(sub))
+
+                    def emit(lo, hi, out, x0, a=a, n=len(sub)):
+                        ex.send[lo:hi, a - lo_t:a - lo_t + n] = out.reshape((hi - lo, n) + tail)
+                        if ex.send_x0 is not None:
+                            ex.send_x0[lo:hi, a - lo_t:a - lo_t + n] = x0.reshape((hi - lo, n) + tail)
+
+                    denoise(i, parity, a, sub, nz, cs, ccs, emit)
+                works = []
+                if world > 1:
+                    # exchange step: ONE pre-sized all-gather of the tiles every rank wrote (a gather, never a reduction)
+                    works.append(dist.all_gather_into_tensor(ex.recv.flatten(0, 1), ex.send, group=group, async_op=True))
+                    if ex.send_x0 is not None:
+                        works.append(dist.all_gather_into_tensor(ex.recv_x0.flatten(0, 1), ex.send_x0, group=group,
+                                                                 async_op=True))
+                if parity == 1:
+                    fresh = ops.randn((1,) + tuple(img.shape[1:]), dev)      # overlaps the exchange
+                for w in works:
+                    w.wait()
+                for r, (lo_r, hi_r) in enumerate(ex.ranges):
+                    if hi_r > lo_r:
+                        for k in range(n_img):
+                            ops.scatter(img[k:k + 1], tiles[lo_r:hi_r], ex.recv[r, k, :hi_r - lo_r], tile)
+                            if x_start is not None:
+                                ops.scatter(x_start[k:k + 1], tiles[lo_r:hi_r], ex.recv_x0[r, k, :hi_r - lo_r], tile)
+            if parity == 1:
+                # outside the hull of the shifted grid the state is replaced by fresh noise at the next noise level
+                # (q_sample of zeros, model.py:3392-3396); the draw covers the whole canvas like the reference's
+                if fresh is None:
+                    fresh = ops.randn((1,) + tuple(img.shape[1:]), dev)
+                sig = ops.sigma(steps[i + 1])
+                for k in range(n_img):
+                    ops.renoise_outside(img[k:k + 1], fresh, sig, plan.inner)
+            if on_step is not None:
+                on_step(i, img, x_start)
+    finally:
+        if prev_invariant is not None:
+            ops.set_batch_invariant(prev_invariant)
     return img, x_start

@@ -1,7 +1,9 @@
 """CPU tests of the large-image orchestration (srgd_b200/tiled.py): the product's `run_tiled` loop driven by a
-plain-torch ops stand-in must reproduce the oracle's tiled_sample (model.py:3288-3413) bit for bit -- in one
-process and with the tiles of every step sharded over 2 / 3 gloo ranks (all-gather of the written tiles per step,
-replicated RNG)."""
+plain-torch ops stand-in must reproduce the oracle's tiled_sample (model.py:3288-3413) bit for bit in one process
+(the reference's minibatch partition), and -- in tile-granular exact mode (`shard=True`: contiguous tile ranges per
+rank, regrouped denoiser calls, one all_gather_into_tensor per step, replicated RNG) -- yield the same image on
+1, 2 and 3 gloo ranks bit for bit.  The exact mode needs a denoiser whose rows do not depend on their batch
+(the library's batch-invariant mode on the GPU); the CPU stand-in gets that by denoising row by row."""
 import os
 import socket
 
@@ -22,13 +24,22 @@ SPEC = O.UnetSpec(dim=16)
 class TorchOps:
     """ops interface of run_tiled on CPU tensors; the denoiser is the oracle's p_sample."""
 
-    def __init__(self, sd, gen):
-        self.sd, self.gen = sd, gen
+    def __init__(self, sd, gen, row_by_row=False):
+        self.sd, self.gen, self.row_by_row = sd, gen, row_by_row
+        self.invariant_calls = []
+
+    def set_batch_invariant(self, on):
+        self.invariant_calls.append(bool(on))
+        return False
 
     def randn(self, shape, device):
         return torch.randn(shape, generator=self.gen)
 
     def p_sample(self, xt, t, ct, label, cs, ccs, t_next, noise):
+        if self.row_by_row:                      # batch-invariant stand-in: a row never sees its batch neighbours
+            rows = [O.p_sample(self.sd, SPEC, xt[k:k + 1], t, ct[k:k + 1], label, cs, ccs, t_next,
+                               noise=None if noise is None else noise[k:k + 1]) for k in range(xt.shape[0])]
+            return torch.cat([r[0] for r in rows], 0), torch.cat([r[1] for r in rows], 0)
         return O.p_sample(self.sd, SPEC, xt, t, ct, label, cs, ccs, t_next, noise=noise)
 
     def gather(self, canvas, coords, tile):
@@ -54,7 +65,7 @@ def _inputs():
     return cond01, torch.tensor([1])
 
 
-def _product_path(sd, shard):
+def _product_path(sd, shard, max_rows=64):
     """What ConditionalContinuousTimeGaussianDiffusionSR.tiled_sample does around run_tiled, on CPU tensors."""
     cond01, label = _inputs()
     gen = torch.Generator().manual_seed(71)
@@ -66,8 +77,10 @@ def _product_path(sd, shard):
     cond_canvas = torch.zeros_like(cond)
     cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
     steps = torch.linspace(1., 0., STEPS + 1)
-    img, _ = run_tiled(TorchOps(sd, gen), img, cond_canvas, plan, steps, STEPS, BATCH, label, 1.0, 0, 2.0, 0, 0,
-                       shard=shard)
+    ops = TorchOps(sd, gen, row_by_row=shard)
+    img, _ = run_tiled(ops, img, cond_canvas, plan, steps, STEPS, BATCH, label, 1.0, 0, 2.0, 0, 0,
+                       shard=shard, max_rows=max_rows)
+    assert ops.invariant_calls == ([True, False] if shard else [])      # switched on for the loop, restored after
     top, bottom, left, right = plan.crop
     return (img[:, :, top:bottom, left:right].clamp(-1, 1) + 1) * 0.5
 
@@ -104,15 +117,29 @@ def test_run_tiled_matches_oracle_single_process():
     assert torch.equal(_product_path(sd, shard=False), _reference(sd))
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_run_tiled_sharded_over_gloo_is_bit_identical(world):
+def test_run_tiled_exact_mode_single_process():
+    """shard=True without a process group: the regrouped calls (any max_rows) give one and the same image, which
+    differs from the reference's minibatch partition only by the CPU conv's batch-dependent blocking (<= 5e-4)."""
     torch.set_num_threads(2)
     sd = O.make_state_dict(SPEC, 11)
-    ref = _reference(sd)
+    a = _product_path(sd, shard=True, max_rows=64)
+    b = _product_path(sd, shard=True, max_rows=3)
+    assert torch.equal(a, b)
+    torch.testing.assert_close(a, _reference(sd), rtol=0, atol=5e-4)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_run_tiled_sharded_over_gloo_is_bit_identical(world):
+    """20 / 12 tiles per step over 2 / 3 ranks (contiguous ranges of 10+10 / 7+7+6 and 6+6 / 4+4+4 tiles): every
+    replica ends with the single-process exact-mode image, bit for bit."""
+    torch.set_num_threads(2)
+    sd = O.make_state_dict(SPEC, 11)
+    single = _product_path(sd, shard=True)
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
-        assert torch.equal(ret[r], ref), f"rank {r} differs from the single-process reference"
+        assert torch.equal(ret[r], single), f"rank {r} differs from the single-process exact-mode run"
+    torch.testing.assert_close(single, _reference(sd), rtol=0, atol=5e-4)
 
 
 def _multi_image_path(sd, conds01, label, max_rows, nsteps):
@@ -169,8 +196,8 @@ def _multi_worker(rank, world, port, ret):
         cond_canvas = torch.zeros_like(cond)
         cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
         steps = torch.linspace(1., 0., 3)
-        img, _ = run_tiled(TorchOps(sd, gen), img, cond_canvas, plan, steps, 2, BATCH, torch.tensor([2]), 1.0, 0, 2.0, 0,
-                           0, shard=(world > 1), max_rows=64)
+        img, _ = run_tiled(TorchOps(sd, gen, row_by_row=True), img, cond_canvas, plan, steps, 2, BATCH,
+                           torch.tensor([2]), 1.0, 0, 2.0, 0, 0, shard=True, max_rows=64)
         ret[rank] = img.clone()
         if world > 1:
             dist.barrier()
@@ -179,8 +206,8 @@ def _multi_worker(rank, world, port, ret):
 
 
 def test_run_tiled_many_images_sharded_over_gloo():
-    """Two images advancing together with the minibatches of every step split over two gloo ranks: both replicas end
-    with the canvases of the single-process run (same stacked batches per minibatch -> bit-identical)."""
+    """Two images advancing together with the tiles of every step split over two gloo ranks: both replicas end
+    with the canvases of the single-process exact-mode run, bit for bit."""
     ret = mp.Manager().dict()
     mp.spawn(_multi_worker, args=(1, _free_port(), ret), nprocs=1, join=True)
     single = ret[0]
