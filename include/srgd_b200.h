@@ -296,6 +296,9 @@ enum {
   SRGD_PK_OTHER = 6,       /* pack_input, final_conv, embeddings, q_sample…  */
   SRGD_PK_COUNT = 7
 };
+/* Number of kernels this library has launched from the calling thread since it was loaded (bench.py `gpu_launches`). */
+long long srgd_launch_count(void);
+
 /* Batch-invariant reductions (returns the previous setting).  The only reduction of the path whose partition depends
  * on the launch's batch size is the LinearAttention context k.softmax(N) v^T (model.py:317-320): its per-sample partials
  * are split over SMs / B thread blocks.  With `on` != 0 the split of a fixed reference batch is used instead, so a row's

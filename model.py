@@ -7,6 +7,7 @@ reference model.py:3503-3515 + 3634-3651): `ConditionalSRUnet` and
 NotImplementedError (no configuration or weights ship for them).
 """
 import copy
+import os
 
 import torch
 import torch.nn as nn
@@ -31,9 +32,10 @@ class ModelEma(nn.Module):
     """Inference-time stand-in for timm.utils.ModelEmaV2 (reference model.py:3657): holds an eval()
     deep copy as `.module`.  The EMA update itself is training-only and not provided."""
 
-    def __init__(self, model, decay=0.9999, device=None):
+    def __init__(self, model, decay=0.9999, device=None, copy_model=True):
         super().__init__()
-        self.module = copy.deepcopy(model).eval()
+        # copy_model=False: take ownership instead of deep-copying 550 MB (get_model keeps no other reference)
+        self.module = (copy.deepcopy(model) if copy_model else model).eval()
         self.decay = decay
         if device is not None:
             self.module.to(device)
@@ -47,11 +49,21 @@ def get_model(conf, logger):
     assert conf.learned_sinusoidal_cond
     dim_mults = tuple(int(v) for v in str(conf.ddpm_unet_dim_mults).split(','))
     full_attn = tuple(v.strip() == 'True' for v in str(conf.full_attn).split(','))
+    from srgd_b200 import weights as _weights
+    from srgd_b200.arch import UnetSpec
+    ckpt_path = conf.ckpt_path or None
+    # ingest cache: the packed device weights of an earlier start of this checkpoint
+    spec = UnetSpec(dim=conf.unet_dim, dim_mults=dim_mults, full_attn=full_attn,
+                    learned_sinusoidal_dim=conf.learned_sinusoidal_dim, num_classes=conf.num_classes)
+    use_cache = bool(ckpt_path) and os.environ.get("SRGD_B200_PACK_CACHE", "1") != "0"
+    cached = _weights.load_pack_cache(ckpt_path, spec) if use_cache else None
     unet = ConditionalSRUnet(dim=conf.unet_dim, dim_mults=dim_mults, full_attn=full_attn,
                              learned_variance=conf.learned_variance,
                              learned_sinusoidal_cond=conf.learned_sinusoidal_cond,
                              learned_sinusoidal_dim=conf.learned_sinusoidal_dim, flash_attn=conf.flash_attn,
-                             pixel_shuffle_upsample=conf.pixel_shuffle_upsample, num_classes=conf.num_classes)
+                             pixel_shuffle_upsample=conf.pixel_shuffle_upsample, num_classes=conf.num_classes,
+                             _init_weights=not ckpt_path)
+    assert unet.spec == spec
     logger.info(f"ConditionalSRUnet: channels=6 dim={conf.unet_dim} dim_mults={conf.ddpm_unet_dim_mults} "
                 f"num_classes={conf.num_classes}")
     conf.use_dpmpp_solver = False
@@ -65,10 +77,16 @@ def get_model(conf, logger):
         loss_type=conf.loss_type)
     logger.info(f"ConditionalContinuousTimeGaussianDiffusionSR: image_size={conf.image_size} "
                 f"num_sample_steps={conf.num_sample_steps}")
-    ema_model = ModelEma(diffusion, decay=conf.ema_decay)
-    if conf.ckpt_path:
-        ckpt = torch.load(conf.ckpt_path, map_location='cpu', weights_only=True)
+    ema_model = ModelEma(diffusion, decay=conf.ema_decay, copy_model=False)
+    if ckpt_path and cached is not None:
+        ema_model.module.model.attach_pack_cache(cached, ckpt_path)
+        logger.info(f"load ema_model weight from : {ckpt_path} (ingest cache {_weights.pack_cache_path(ckpt_path)}; "
+                    "fp32 parameters are read from the checkpoint on first state_dict())")
+    elif ckpt_path:
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=True)
         check = ema_model.module.load_state_dict(ckpt['ema_model'], strict=conf.load_strict)
-        logger.info(f"load ema_model weight from : {conf.ckpt_path}")
+        logger.info(f"load ema_model weight from : {ckpt_path}")
         logger.info(f"check: {check}")
+        if use_cache and not check.missing_keys and not check.unexpected_keys:
+            ema_model.module.model.save_pack_cache_after_first_pack(ckpt_path)
     return ema_model

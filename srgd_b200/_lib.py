@@ -106,6 +106,7 @@ SIGNATURES = {
     "srgd_unet_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _SZ, _I32, _P]),
     "srgd_unet_set_tap": (C.c_int, [_P, C.c_char_p, _P, _SZ]),
     "srgd_unet_last_launch_count": (C.c_int, [_P]),
+    "srgd_launch_count": (C.c_longlong, []),
     "srgd_set_batch_invariant": (C.c_int, [C.c_int]),
     "srgd_profile_begin": (C.c_int, []),
     "srgd_profile_end": (C.c_int, []),

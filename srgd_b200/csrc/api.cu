@@ -117,6 +117,8 @@ int srgd_device_check(int device) {
   return rc;
 }
 
+long long srgd_launch_count(void) { return (long long)srgd::g_launches; }
+
 int srgd_set_batch_invariant(int on) {
   const int prev = srgd::g_batch_invariant;
   srgd::g_batch_invariant = on ? 1 : 0;

@@ -281,10 +281,12 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
     def tiled_sample(self, batch_size=4, tile_size=256, tile_stride=256, condition_x=None, class_label=None,
                      cond_scale=1.0, guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
                      generation_start_steps=0, num_sample_steps=None, with_images=False, with_x0_images=False,
-                     start_white_noise=True, amp=False, shard_tiles=False):
-        """`shard_tiles=True` (extension): with an initialised torch.distributed group the tiles of every step are
-        split over the ranks and exchanged once per step; every rank returns the same image, bit-identical to the
-        single-GPU result (srgd_b200/tiled.py).
+                     start_white_noise=True, amp=False, shard_tiles=False, shard_group=None):
+        """`shard_tiles=True` (extension, srgd_b200/tiled.py "exact mode"): the tiles of every step are split into
+        contiguous ranges over the ranks of the initialised torch.distributed group (`shard_group`, default: the world)
+        and exchanged with one all-gather per step; denoiser calls are regrouped (up to 64 rows instead of
+        `batch_size`) with the library in batch-invariant mode, so every rank returns the same image, bit-identical
+        for every world size (1 included).  `batch_size` then only shapes the noise draws, as in the reference.
 
         `condition_x` with a batch of N > 1 same-sized images (extension; the reference's loop only works for N = 1):
         the images advance together, their tiles stacked into one denoiser batch, and share ONE noise stream -- the
@@ -334,7 +336,7 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
         img, x_start = run_tiled(CudaTiledOps(self), img, cond_canvas, plan, steps, num_sample_steps, batch_size,
                                  class_label, cond_scale, guidance_start_steps, class_cond_scale,
                                  class_guidance_start_steps, generation_start_steps, x_start=x_start, on_step=on_step,
-                                 shard=shard_tiles)
+                                 shard=shard_tiles, group=shard_group)
         for _ in bar_it:
             pass
         img = self._finalize(img[:, :, top:bottom, left:right].contiguous())

@@ -57,7 +57,7 @@ class ConditionalSRUnet(nn.Module):
                  self_condition=True, resnet_block_groups=8, learned_variance=False,
                  learned_sinusoidal_cond=False, random_fourier_features=False, learned_sinusoidal_dim=16,
                  attn_dim_head=32, attn_heads=4, full_attn=(False, False, False, True), flash_attn=False,
-                 pixel_shuffle_upsample=True, num_classes=None):
+                 pixel_shuffle_upsample=True, num_classes=None, _init_weights=True):
         super().__init__()
         unsupported = []
         if init_dim not in (None, dim): unsupported.append("init_dim != dim")
@@ -85,8 +85,15 @@ class ConditionalSRUnet(nn.Module):
         self.downsample_factor = self.spec.downsample_factor
         gen = torch.Generator().manual_seed(0)
         for name, shape in unet_keys(self.spec).items():
-            p = nn.Parameter(_init_like_torch(name, shape, gen), requires_grad=False)
-            _attach(self, name, p)
+            # _init_weights=False (get_model with a checkpoint to load): uninitialised storage, no 1.5 s of random init
+            t = _init_like_torch(name, shape, gen) if _init_weights else torch.empty(shape)
+            _attach(self, name, nn.Parameter(t, requires_grad=False))
+        # Ingest cache (weights.load_pack_cache): the packed tensors of an earlier start.  While `_deferred_ckpt` is
+        # set, the fp32 parameters are uninitialised placeholders -- the forward only ever reads the pack -- and are
+        # filled from the checkpoint the first time anybody asks for them (state_dict()).
+        self._cached_pack: Optional[Dict[str, torch.Tensor]] = None
+        self._deferred_ckpt: Optional[str] = None
+        self._save_pack_for: Optional[str] = None
         self._handle = None
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
@@ -98,7 +105,7 @@ class ConditionalSRUnet(nn.Module):
         self.conv_impl = 0          # debug knob: 1 = CUDA-core direct conv, 2 = stand-alone GN statistics
         self.last_launches = 0
 
-    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspaces", "_plist", "_labels_ok")
+    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspaces", "_plist", "_labels_ok", "_save_pack_for")
 
     def __deepcopy__(self, memo):
         # device handles / packed weights are per-instance runtime state: a copy re-packs lazily
@@ -116,13 +123,52 @@ class ConditionalSRUnet(nn.Module):
         return r
 
     def _apply(self, fn, *a, **kw):
-        r = super()._apply(fn, *a, **kw)
+        if self._deferred_ckpt is not None:
+            # placeholders: re-create them where fn would put them instead of copying 550 MB of nothing
+            probe = fn(torch.empty(1, device=next(self.parameters()).device))
+            with torch.no_grad():
+                for p in self.parameters():
+                    p.data = torch.empty(p.shape, device=probe.device, dtype=probe.dtype)
+            r = self
+        else:
+            r = super()._apply(fn, *a, **kw)
         self._drop_handle()
         return r
 
     @staticmethod
     def _after_load(module, incompatible_keys) -> None:
+        module._cached_pack = None               # new weights: an attached ingest cache no longer describes them
+        module._deferred_ckpt = None
         module._drop_handle()
+
+    def attach_pack_cache(self, pack: Dict[str, torch.Tensor], ckpt_path: str) -> None:
+        """Start from the ingest cache of `ckpt_path` (weights.load_pack_cache) instead of its fp32 state dict."""
+        self._drop_handle()
+        self._cached_pack, self._deferred_ckpt = pack, ckpt_path
+
+    def save_pack_cache_after_first_pack(self, ckpt_path: str) -> None:
+        self._save_pack_for = ckpt_path
+
+    def _materialize(self) -> None:
+        """Fill the placeholder parameters from the checkpoint the ingest cache was made from."""
+        if self._deferred_ckpt is None:
+            return
+        path, self._deferred_ckpt = self._deferred_ckpt, None
+        sd = torch.load(path, map_location="cpu", weights_only=True)["ema_model"]
+        own = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+        pack, handle_state = self._cached_pack, (self._handle, self._packed, self._packed_key)
+        with torch.no_grad():
+            for k, p in super().state_dict(keep_vars=True).items():
+                p.data.copy_(own[k])
+        # same weights as the pack: keep using it (copy_ bumped the version counters, so refresh the key)
+        self._cached_pack = pack
+        self._handle, self._packed, _ = handle_state
+        if self._handle is not None:
+            self._packed_key = self._weights_key(self._packed_key[0])
+
+    def state_dict(self, *a, **kw):
+        self._materialize()
+        return super().state_dict(*a, **kw)
 
     def _drop_handle(self):
         if getattr(self, "_handle", None) is not None:
@@ -162,8 +208,14 @@ class ConditionalSRUnet(nn.Module):
         _lib.check(lib.srgd_device_check(device.index if device.index is not None else torch.cuda.current_device()),
                    "srgd_device_check")
         with torch.cuda.device(device):
-            sd = {k: v for k, v in self.state_dict().items()}
-            packed = weights.pack(self.spec, sd, device)
+            if self._cached_pack is not None:
+                packed = {k: v.to(device, non_blocking=False) for k, v in self._cached_pack.items()}
+            else:
+                sd = {k: v for k, v in self.state_dict().items()}
+                packed = weights.pack(self.spec, sd, device)
+                if self._save_pack_for is not None:
+                    path, self._save_pack_for = self._save_pack_for, None
+                    weights.save_pack_cache(path, self.spec, packed)
             names = weights.param_names(self.spec)
             missing = [n for n in names if n not in packed]
             if missing:

@@ -13,8 +13,10 @@ Pure data movement (permutes, casts, concatenations) done once per load with tor
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import math
-from typing import Dict, List
+import os
+from typing import Dict, List, Optional
 
 import torch
 
@@ -145,3 +147,78 @@ def pack(spec: UnetSpec, sd: Dict[str, torch.Tensor], device: torch.device) -> D
     out["final.w"] = f32(g("final_conv.weight").reshape(spec.channels, spec.dim))
     out["final.b"] = f32(g("final_conv.bias"))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ingest cache.  The reference pays `torch.load` of the 550 MB fp32 checkpoint plus module
+# construction on every start (model.py:3657-3664); here the packed tensors of pack() -- ~276 MB, bf16 K-major conv
+# weights, fused embedding matrices, the evaluated class table -- are written next to the checkpoint after the first
+# load and memory-mapped on later starts, which then skip torch.load, load_state_dict and the repack.
+# ---------------------------------------------------------------------------------------------------
+PACK_FORMAT = 2                      # bump whenever pack()'s output layout changes
+
+
+def pack_cache_path(ckpt_path: str) -> str:
+    return ckpt_path + ".srgd_b200_pack"
+
+
+def file_sha256(path: str) -> str:
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 24), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def _ckpt_identity(ckpt_path: str) -> Dict[str, int]:
+    st = os.stat(ckpt_path)
+    return dict(size=int(st.st_size), mtime_ns=int(st.st_mtime_ns))
+
+
+def _spec_key(spec: UnetSpec) -> str:
+    return repr((spec.dim, tuple(spec.dim_mults), spec.channels, spec.groups, spec.learned_sinusoidal_dim, spec.heads,
+                 spec.dim_head, tuple(spec.full_attn), spec.num_classes))
+
+
+def save_pack_cache(ckpt_path: str, spec: UnetSpec, packed: Dict[str, torch.Tensor]) -> Optional[str]:
+    """Writes <ckpt>.srgd_b200_pack (atomically).  The cache is keyed by the checkpoint's sha256, recorded together
+    with its size / mtime so that later starts can validate it without re-reading 550 MB.  Returns the path, or None
+    if the directory is not writable."""
+    path = pack_cache_path(ckpt_path)
+    blob = dict(format=PACK_FORMAT, spec=_spec_key(spec), sha256=file_sha256(ckpt_path), **_ckpt_identity(ckpt_path),
+                tensors={k: v.detach().to("cpu").contiguous() for k, v in packed.items()})
+    tmp = f"{path}.tmp{os.getpid()}"
+    try:
+        torch.save(blob, tmp)
+        os.replace(tmp, path)
+    except OSError:
+        try:
+            os.unlink(tmp)
+        except OSError:
+            pass
+        return None
+    return path
+
+
+def load_pack_cache(ckpt_path: str, spec: UnetSpec, verify_sha256: Optional[bool] = None):
+    """The cached pack {name: CPU tensor (memory-mapped)} of `ckpt_path`, or None when there is no valid cache: missing
+    file, other pack format / architecture, or a checkpoint whose size or mtime changed (then the sha256 decides: an
+    identical file that was merely copied or touched keeps its cache).  SRGD_B200_VERIFY_CACHE=1 re-hashes always."""
+    path = pack_cache_path(ckpt_path)
+    if not os.path.exists(path) or not os.path.exists(ckpt_path):
+        return None
+    try:
+        blob = torch.load(path, map_location="cpu", weights_only=True, mmap=True)
+    except Exception:
+        return None
+    if not isinstance(blob, dict) or blob.get("format") != PACK_FORMAT or blob.get("spec") != _spec_key(spec):
+        return None
+    if verify_sha256 is None:
+        verify_sha256 = os.environ.get("SRGD_B200_VERIFY_CACHE", "0") == "1"
+    ident = _ckpt_identity(ckpt_path)
+    same_stat = blob.get("size") == ident["size"] and blob.get("mtime_ns") == ident["mtime_ns"]
+    if blob.get("size") != ident["size"]:
+        return None
+    if (verify_sha256 or not same_stat) and file_sha256(ckpt_path) != blob.get("sha256"):
+        return None
+    return blob["tensors"]

@@ -2,8 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/gpu_multi_check.py
 
-  1. tiled_sample(shard_tiles=True): the tiles of every step split over the ranks with one all-gather per step must
-     give every rank the image the single-GPU run produces, bit for bit;
+  1. tiled_sample(shard_tiles=True) (exact mode): contiguous tile ranges per rank + one all-gather per step must give
+     every rank the image the same mode produces on ONE GPU, bit for bit (dim-128 U-Net, 768^2 and 2304^2 canvases);
+     the difference to the reference's minibatch partition (fp32 re-association only) is printed;
   2. sample_sharded: batch rows split over the ranks + one final gather == the single-GPU sample() with replicated RNG.
 """
 import os
@@ -24,25 +25,38 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    spec = O.UnetSpec(dim=64)
-    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    solo = [dist.new_group([r]) for r in range(world)][rank]                 # a group of this rank alone = "1 GPU"
+    spec = O.UnetSpec()
+    unet = M.ConditionalSRUnet(dim=128, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
     diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=256, num_sample_steps=6)
-    diff.load_state_dict(O.make_state_dict(spec, 22), strict=True)
+    diff.load_state_dict(O.make_state_dict(spec, 1234, init="torch"), strict=True)
     diff = diff.eval().to(dev)
     diff.progress = False
     g = torch.Generator().manual_seed(5)
-    cond01 = torch.rand(1, 3, 288, 320, generator=g).to(dev)                 # canvas 768x768: 9 / 4 tiles per step
     label = torch.tensor([2], device=dev)
-    outs = {}
-    for shard in (False, True):
-        torch.manual_seed(71)
-        torch.cuda.manual_seed(71)
-        outs[shard] = diff.tiled_sample(batch_size=2, condition_x=cond01, class_label=label, class_cond_scale=3.0,
-                                        num_sample_steps=6, shard_tiles=shard)
-    same = bool(torch.equal(outs[False], outs[True]))
-    flags = [None] * world
-    dist.all_gather_object(flags, same)
+    flags_all = []
+    # 768^2 canvas (9 / 4 tiles per step) and config 4's 2304^2 canvas (81 / 64 tiles per step), full-width U-Net
+    for hw, bs in (((288, 320), 2), ((2048, 2048), 8)):
+        cond01 = torch.rand(1, 3, hw[0] // 4, hw[1] // 4, generator=g)
+        cond01 = torch.nn.functional.interpolate(cond01, size=hw, mode="bicubic", align_corners=False).clamp(0, 1).to(dev)
+        outs = {}
+        for mode, kw in (("reference partition", dict(shard_tiles=False)),
+                         ("exact mode, this rank alone", dict(shard_tiles=True, shard_group=solo)),
+                         (f"exact mode, {world} ranks", dict(shard_tiles=True))):
+            torch.manual_seed(71)
+            torch.cuda.manual_seed(71)
+            outs[mode] = diff.tiled_sample(batch_size=bs, condition_x=cond01, class_label=label, class_cond_scale=3.0,
+                                           num_sample_steps=6, **kw)
+        a, b, c = outs.values()
+        same = bool(torch.equal(b, c))
+        flags = [None] * world
+        dist.all_gather_object(flags, same)
+        flags_all += flags
+        if rank == 0:
+            print(f"{hw[0]}x{hw[1]} HR, world {world}: exact mode on {world} ranks == exact mode on 1 GPU, per rank: {flags}; "
+                  f"exact mode vs the reference's minibatch partition: max-abs {float((a - b).abs().max()):.2e}", flush=True)
     # batch sharding
+    flags = flags_all
     cond_b = torch.rand(5, 3, 64, 64, generator=g).to(dev)
     diff64 = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=64, num_sample_steps=6)
     diff64.progress = False

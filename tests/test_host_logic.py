@@ -240,3 +240,44 @@ def test_seeded_state_dict_equals_the_oracles(init):
     a, b = arch.seeded_state_dict(spec_p, 1234, init=init), O.make_state_dict(spec_o, 1234, init=init)
     assert list(a) == list(b)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_ingest_cache_validation_and_deferred_fp32(tmp_path):
+    """SURVEY section 8 f-3: <ckpt>.srgd_b200_pack is keyed by the checkpoint's sha256 (size / mtime as the fast check);
+    a start from the cache leaves the fp32 parameters as placeholders until somebody asks for state_dict()."""
+    import logging
+    import config as Cfg
+    import model as M
+    from srgd_b200 import weights
+    spec = arch.UnetSpec(dim=64)
+    sd = arch.seeded_state_dict(spec, 5, init="torch")
+    ckpt = str(tmp_path / "m.pth")
+    torch.save({"ema_model": sd}, ckpt)
+    fake_pack = {"init.w": torch.arange(12.).reshape(3, 4).bfloat16(), "init.b": torch.ones(3)}
+    assert weights.load_pack_cache(ckpt, spec) is None
+    assert weights.save_pack_cache(ckpt, spec, fake_pack) == weights.pack_cache_path(ckpt)
+    got = weights.load_pack_cache(ckpt, spec)
+    assert got is not None and all(torch.equal(got[k], v) for k, v in fake_pack.items())
+    assert weights.load_pack_cache(ckpt, arch.UnetSpec(dim=128)) is None            # other architecture
+    os.utime(ckpt, ns=(1, 1))                                                        # touched, same bytes: sha decides
+    assert weights.load_pack_cache(ckpt, spec) is not None
+    sd2 = dict(sd)
+    sd2["model.final_conv.bias"] = sd["model.final_conv.bias"] + 1                   # same size, other contents
+    torch.save({"ema_model": sd2}, ckpt)
+    assert weights.load_pack_cache(ckpt, spec) is None
+    # get_model from the cache: no torch.load of the fp32 checkpoint until state_dict() is requested
+    weights.save_pack_cache(ckpt, spec, fake_pack)
+    yaml_path = tmp_path / "c.yaml"
+    yaml_path.write_text("model: conditional_continuous\nunet_dim: 64\nimage_size: 64\nnum_sample_steps: 250\n"
+                         "learned_sinusoidal_cond: true\nlearned_sinusoidal_dim: 32\n")
+    conf = Cfg.load_config(str(yaml_path))
+    conf.ckpt_path = ckpt
+    ema = M.get_model(conf, logging.getLogger("t"))
+    unet = ema.module.model
+    assert unet._deferred_ckpt == ckpt and unet._cached_pack is not None
+    ema.module.to("cpu")                                                             # placeholder-aware _apply
+    full = ema.module.state_dict()
+    assert unet._deferred_ckpt is None and all(torch.equal(full[k], sd2[k]) for k in sd2)
+    # loading other weights detaches the cache
+    ema.module.load_state_dict(sd, strict=True)
+    assert unet._cached_pack is None
