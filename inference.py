@@ -43,6 +43,9 @@ def parse_args(argv=None):
     # throughput extension: consecutive files of equal size are sampled together (their tiles share denoiser batches);
     # every image still sees the noise stream of its own reseeded run, so the outputs do not change
     ap.add_argument('--images_per_batch', type=int, default=1)
+    # large images under torchrun: every rank works on EVERY image and denoises a contiguous range of its tiles, with
+    # one all-gather per step (tiled_sample's exact mode: the image does not depend on the number of GPUs)
+    ap.add_argument('--shard_tiles', action='store_true')
     return ap.parse_args(argv)
 
 
@@ -68,25 +71,49 @@ def _to_image(t: torch.Tensor) -> Image.Image:
     return Image.fromarray(arr, mode='RGB')
 
 
-def sr_target_images(images, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
-                     class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
-                     num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71):
-    """The per-image pipeline of the reference (inference.py:59-98) for a list of equally sized PIL images."""
+def _prepare(images, scale=4):
+    """PIL bicubic pre-upscale + ToTensor of equally sized images (inference.py:66-74) -> float [N,3,4h,4w] in [0,1],
+    in pinned host memory when CUDA is present (an asynchronous H2D copy then overlaps the previous image's work)."""
     width, height = images[0].size
     assert all(im.size == (width, height) for im in images)
     # the reference maps both 'bicubic' and 'lanczos' to bicubic (inference.py:66-69)
-    condition_x = torch.cat([_to_unit_tensor(im.resize((width * scale, height * scale), resample=Image.BICUBIC))
-                             for im in images]).to(sr_model.device)
+    cond = torch.cat([_to_unit_tensor(im.resize((width * scale, height * scale), resample=Image.BICUBIC))
+                      for im in images])
+    if torch.cuda.is_available():
+        try:
+            cond = cond.pin_memory()
+        except RuntimeError:
+            pass
+    return cond
+
+
+def _sample(condition_x, sr_model, batch_size, test_label, cond_scale, guidance_start_steps, class_cond_scale,
+            class_guidance_start_steps, generation_start_steps, num_sample_steps, enable_amp, seed, shard_tiles=False):
+    """seed + tiled_sample (inference.py:77-92); returns the device result as uint8 [N,H,W,3] with ToPILImage's
+    mul(255).byte() truncation (inference.py:94) -- a quarter of the float bytes to bring back."""
+    condition_x = condition_x.to(sr_model.device, non_blocking=True)
     label = None if test_label is None else torch.tensor([test_label], dtype=torch.long, device=sr_model.device)
     seed_everything(seed)
+    kw = dict(shard_tiles=True) if shard_tiles else {}
     with torch.inference_mode():
         output = sr_model.tiled_sample(batch_size=batch_size, condition_x=condition_x, class_label=label,
                                        cond_scale=cond_scale, guidance_start_steps=guidance_start_steps,
                                        class_cond_scale=class_cond_scale,
                                        class_guidance_start_steps=class_guidance_start_steps,
                                        generation_start_steps=generation_start_steps,
-                                       num_sample_steps=num_sample_steps, amp=enable_amp)
-    outs = [_to_image(o) for o in output]
+                                       num_sample_steps=num_sample_steps, amp=enable_amp, **kw)
+        return output.detach().mul(255).byte().permute(0, 2, 3, 1).contiguous()
+
+
+def sr_target_images(images, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0, guidance_start_steps=0,
+                     class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
+                     num_sample_steps=250, enable_amp=False, interpolation='bicubic', seed=71, shard_tiles=False):
+    """The per-image pipeline of the reference (inference.py:59-98) for a list of equally sized PIL images."""
+    width, height = images[0].size
+    u8 = _sample(_prepare(images, scale), sr_model, batch_size, test_label, cond_scale, guidance_start_steps,
+                 class_cond_scale, class_guidance_start_steps, generation_start_steps, num_sample_steps, enable_amp,
+                 seed, shard_tiles)
+    outs = [Image.fromarray(a, mode='RGB') for a in u8.cpu().numpy()]
     assert all(o.size == (width * 4, height * 4) for o in outs)
     return outs
 
@@ -109,26 +136,10 @@ def try_open_image(image_path):
         return None
 
 
-def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0,
-                           guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
-                           generation_start_steps=0, num_sample_steps=250, start_index=0, end_index=None,
-                           enable_amp=False, interpolation='bicubic', seed=71, world_size=1, rank=0,
-                           images_per_batch=1):
-    print(f"save images at: {output_dir}")
-    os.makedirs(output_dir, exist_ok=True)
-    files = sorted(glob.glob(f"{input_dir}/*"))[start_index:end_index][rank::world_size]
-    kw = dict(scale=scale, batch_size=batch_size, test_label=test_label, cond_scale=cond_scale,
-              guidance_start_steps=guidance_start_steps, class_cond_scale=class_cond_scale,
-              class_guidance_start_steps=class_guidance_start_steps, generation_start_steps=generation_start_steps,
-              num_sample_steps=num_sample_steps, enable_amp=enable_amp, interpolation=interpolation, seed=seed)
-    pending = []                                   # (image, save_path) of consecutive equally sized inputs
-
-    def flush():
-        if pending:
-            for out, (_, save_path) in zip(sr_target_images([im for im, _ in pending], sr_model, **kw), pending):
-                out.save(save_path)
-            pending.clear()
-
+def _work_groups(files, output_dir, images_per_batch):
+    """The reference's directory walk (inference.py:120-142: sorted files, skip existing outputs, skip unreadable
+    files) as a generator of groups [(image, save_path), ...] of consecutive equally sized inputs."""
+    pending = []
     for path in files:
         save_path = os.path.join(output_dir, os.path.basename(path).replace('.png', '_out.png'))
         if os.path.exists(save_path):           # doubles as resume-after-crash (inference.py:126)
@@ -139,9 +150,94 @@ def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=
             print('Invalid image or unable to open image:', path)
             continue
         if pending and (image.size != pending[0][0].size or len(pending) >= images_per_batch):
-            flush()
+            yield pending
+            pending = []
         pending.append((image, save_path))
-    flush()
+    if pending:
+        yield pending
+
+
+def batch_sr_target_images(input_dir, output_dir, sr_model, scale=4, batch_size=8, test_label=2, cond_scale=1.0,
+                           guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                           generation_start_steps=0, num_sample_steps=250, start_index=0, end_index=None,
+                           enable_amp=False, interpolation='bicubic', seed=71, world_size=1, rank=0,
+                           images_per_batch=1, shard_tiles=False):
+    """The directory loop (inference.py:108-142) as a three-stage pipeline, so the GPU never waits for PIL:
+
+      loader thread : open + RGB convert + bicubic x4 + ToTensor into pinned memory, one group ahead of the sampler
+      main thread   : H2D (async from pinned), reseed, tiled_sample, mul(255).byte() on the device, D2H of the uint8
+                      result into a pinned buffer on a side stream
+      saver thread  : waits for that copy's event, PNG-encodes and writes <name>_out.png
+
+    The order of sampling, the per-image reseed and the pixels are those of the sequential loop."""
+    import queue
+    import threading
+    print(f"save images at: {output_dir}")
+    os.makedirs(output_dir, exist_ok=True)
+    files = sorted(glob.glob(f"{input_dir}/*"))[start_index:end_index]
+    if not shard_tiles:
+        files = files[rank::world_size]         # images over ranks; with shard_tiles every rank works on every image
+    use_cuda = sr_model.device.type == 'cuda'
+    ready: "queue.Queue" = queue.Queue(maxsize=2)
+    to_save: "queue.Queue" = queue.Queue(maxsize=4)
+    failure = []
+
+    def loader():
+        try:
+            for group in _work_groups(files, output_dir, images_per_batch):
+                ready.put((group, _prepare([im for im, _ in group], scale)))
+        except BaseException as e:              # surfaced by the main thread
+            failure.append(e)
+        finally:
+            ready.put(None)
+
+    def saver():
+        while True:
+            item = to_save.get()
+            if item is None:
+                return
+            try:
+                host, event, group = item
+                if event is not None:
+                    event.synchronize()
+                for arr, (im, save_path) in zip(host.numpy(), group):
+                    out = Image.fromarray(arr, mode='RGB')
+                    assert out.size == (im.size[0] * 4, im.size[1] * 4)
+                    out.save(save_path)
+            except BaseException as e:
+                failure.append(e)
+
+    threads = [threading.Thread(target=loader, daemon=True), threading.Thread(target=saver, daemon=True)]
+    for t in threads:
+        t.start()
+    copy_stream = torch.cuda.Stream(device=sr_model.device) if use_cuda else None
+    try:
+        while not failure:
+            item = ready.get()
+            if item is None:
+                break
+            group, cond = item
+            u8 = _sample(cond, sr_model, batch_size, test_label, cond_scale, guidance_start_steps, class_cond_scale,
+                         class_guidance_start_steps, generation_start_steps, num_sample_steps, enable_amp, seed,
+                         shard_tiles)
+            if shard_tiles and rank != 0:
+                continue                         # every rank holds the image; rank 0 writes it
+            if use_cuda:
+                host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+                done = torch.cuda.Event()
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    host.copy_(u8, non_blocking=True)
+                    done.record(copy_stream)
+                u8.record_stream(copy_stream)
+                to_save.put((host, done, group))
+            else:
+                to_save.put((u8, None, group))
+    finally:
+        to_save.put(None)
+        threads[1].join()
+    if failure:
+        raise failure[0]
 
 
 def main(argv=None):
@@ -155,6 +251,11 @@ def main(argv=None):
                            "Use the reference implementation for CPU inference.")
     local_rank = int(os.environ.get('LOCAL_RANK', args.rank % max(1, torch.cuda.device_count())))
     torch.cuda.set_device(local_rank)
+    shard = bool(args.shard_tiles) and args.world_size > 1
+    if shard:                                   # one large image at a time, its tiles split over the GPUs of the box
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ema_model = get_model(conf, logger)
     sr_model = ema_model.module.eval().to(torch.device('cuda', local_rank))
     print(args)
@@ -166,7 +267,7 @@ def main(argv=None):
                            num_sample_steps=args.num_sample_steps, start_index=args.start_index,
                            end_index=args.end_index, enable_amp=args.amp, interpolation=args.interpolation,
                            seed=args.seed, world_size=args.world_size, rank=args.rank,
-                           images_per_batch=max(1, args.images_per_batch))
+                           images_per_batch=max(1, args.images_per_batch), shard_tiles=shard)
 
 
 if __name__ == '__main__':
