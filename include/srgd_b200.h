@@ -133,7 +133,16 @@ typedef struct srgd_conv_desc {
   float* gn_partials;      /* NULL, or fp32 [m_tiles][S][8][2], S = samples spanned by one 128-pixel M tile
                               (1 when Ho*Wo >= 128): sum and sum of squares per GroupNorm group of the fp32
                               result (model.py:247) over the pixels of that (M tile, sample)               */
+  void* splitk_ws;         /* NULL, or a device workspace of srgd_conv_splitk_workspace_bytes() bytes whose first
+                              4096 bytes were zeroed once (the kernel re-arms them): when the tiles of a launch leave
+                              the last wave of the persistent grid at most half full, the K loop of those tiles is
+                              split across the idle SMs (fp32 partial accumulators through this workspace, summed in
+                              a fixed order: deterministic).  One workspace serves any number of launches on a stream */
+  int64_t splitk_ws_bytes;
 } srgd_conv_desc;
+
+/* Size of srgd_conv_desc.splitk_ws. */
+size_t srgd_conv_splitk_workspace_bytes(void);
 
 /* Number of 64-byte gn_partials records the kernel writes for (B,Ho,Wo): m_tiles * S. */
 int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo);

@@ -50,7 +50,7 @@ class ConvDesc(C.Structure):
                 ("srcs", ConvSrc * SRGD_CONV_MAX_SRC), ("phases", ConvPhase * SRGD_CONV_MAX_PHASE),
                 ("weight", C.c_void_p), ("Ktot", C.c_int64), ("bias", C.c_void_p), ("row_scale", C.c_void_p),
                 ("residual", C.c_void_p), ("act", C.c_int32), ("out_mode", C.c_int32), ("out", C.c_void_p),
-                ("gn_partials", C.c_void_p)]
+                ("gn_partials", C.c_void_p), ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class UnetConfig(C.Structure):
@@ -77,6 +77,7 @@ SIGNATURES = {
     "srgd_scatter_tiles": (C.c_int, [_P, _P, C.POINTER(TileCoords), _I32, _I32, _I32, _I32, _P]),
     "srgd_renoise_outside": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P]),
     "srgd_conv_m_tiles": (C.c_int, [_I32, _I32, _I32]),
+    "srgd_conv_splitk_workspace_bytes": (_SZ, []),
     "srgd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "srgd_conv_direct": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "srgd_groupnorm_finalize": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),

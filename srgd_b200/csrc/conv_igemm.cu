@@ -60,7 +60,46 @@ struct alignas(64) ConvKernelParams {
   const bf16* residual;
   bf16* out;
   float* gn_partials;
+  // split-K of the partial last wave (conv_igemm_kernel only; split == 1: off).  Work items [0, n_full) are whole
+  // tiles; item n_full + slot * split + part is K part `part` of tile n_full + slot.
+  int16_t ph_iter0[SRGD_CONV_MAX_PHASE];   // linear k-block index at which phase ph starts
+  int32_t n_full, split, kb_per_part, total_items;
+  float* sk_part;                 // helper parts' fp32 accumulators: [slot][part - 1][BN columns][128 rows]
+  int32_t* sk_flags;              // [0, 256): helper-warp arrivals per slot; [256, 512): consumer-warp departures
 };
+
+// Split-K work decomposition.  With T tiles on G persistent CTAs the last wave holds T % G tiles; when that is at
+// most G / 2 the K loop of each of those tiles is cut into `split` parts that run on different CTAs at the same
+// time: part 0 ("main") owns the epilogue, the other parts ("helpers") dump their fp32 accumulators to a workspace
+// and raise a flag.  All items of the split wave are the LAST item of their CTA and every CTA of the grid is
+// resident, so the main part's wait can never deadlock.
+struct WorkItem {
+  int tile, kb0, kb1, part, slot;   // part: -1 = whole tile, 0 = main part, > 0 = helper part
+};
+__device__ __forceinline__ WorkItem decode_item(const ConvKernelParams& p, int item) {
+  WorkItem w;
+  if (item < p.n_full) {
+    w.tile = item; w.kb0 = 0; w.kb1 = p.total_kblocks; w.part = -1; w.slot = 0;
+  } else {
+    const int r = item - p.n_full;
+    w.slot = r / p.split;
+    w.part = r - w.slot * p.split;
+    w.tile = p.n_full + w.slot;
+    w.kb0 = w.part * p.kb_per_part;
+    w.kb1 = min(w.kb0 + p.kb_per_part, p.total_kblocks);
+  }
+  return w;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 constexpr int kMaxBiasSmem = 2048;   // widest conv of the U-Net (pixel-shuffle 1024 -> 2048)
 
@@ -134,7 +173,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     // ===================================== TMA producer =====================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const WorkItem wi = decode_item(p, item);
+      const int tile = wi.tile;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int tx = m_tile % p.tiles_x;
@@ -146,7 +187,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         const int xs = x0 + p.ph_dx[ph], ys = y0 + p.ph_dy[ph];
         const int kblk0 = p.ph_kblk[ph];
         const int ncb = p.ph_cblocks[ph];
-        for (int cb = 0; cb < ncb; ++cb) {
+        const int it0 = p.ph_iter0[ph];                    // this item's share of the phase (whole phase unless split)
+        const int cb_lo = max(0, wi.kb0 - it0), cb_hi = min(ncb, wi.kb1 - it0);
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
@@ -164,11 +207,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const WorkItem wi = decode_item(p, item);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.total_kblocks; ++kb) {
+      for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -177,10 +221,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-          ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - wi.kb0) | k) != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
-        if (kb == p.total_kblocks - 1) ptx::umma_commit(&tfull_bar[acc]);
+        if (kb == wi.kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -215,7 +259,34 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     const int srow = lane >> 2, spiece = lane & 3;         // read-back role: row 8k + srow, piece spiece
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const WorkItem wi = decode_item(p, item);
+      const int tile = wi.tile;
+      if (wi.part > 0) {
+        // -------- split-K helper part: raw fp32 accumulator -> workspace, column-major inside the tile so that a
+        // warp's 32 rows of one column are one 128-byte line; then one release-arrival per warp --------
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row_h = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        float* dst = p.sk_part + ((int64_t)(wi.slot * (p.split - 1) + wi.part - 1) * BN) * 128 + r;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_row_h + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + (c * 32 + j) * 128, __uint_as_float(v[j]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          __threadfence();
+          atomicAdd(p.sk_flags + wi.slot, 1);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float* gn_w = gn_smem + (gn_par * 8 + warp) * kGnRow;   // this warp's staging row for this tile
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -261,6 +332,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const float* sk_src = nullptr;
+      if (wi.part == 0) {
+        // split-K main part: the helper parts of this tile have raised 8 arrivals each (bounded spin, like mbar_wait)
+        if (lane == 0) {
+          const int want = 8 * (p.split - 1);
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(p.sk_flags + wi.slot) < want) {
+            if (clock64() - t0 > 4000000000LL) {
+              printf("srgd_b200: split-K wait timed out (block %d slot %d)\n", (int)blockIdx.x, wi.slot);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+        sk_src = p.sk_part + ((int64_t)(wi.slot * (p.split - 1)) * BN) * 128 + r;
+      }
 
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -269,6 +356,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         ptx::tmem_ld_wait();
         const int nc = n0 + c * 32;                      // first output channel of this chunk
         float f[32];
+        if (sk_src != nullptr) {                         // + the helpers' partial sums, in part order
+          for (int h = 0; h < p.split - 1; ++h) {
+            const float* src = sk_src + ((int64_t)h * BN + c * 32) * 128;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + ld_cg_f32(src + j * 128));
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
         if (bias_staged) {
@@ -365,6 +459,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (wi.part == 0 && lane == 0) {
+        // the last of the 8 consumer warps re-arms the slot's flags for the next launch that uses this workspace
+        if (atomicAdd(p.sk_flags + 256 + wi.slot, 1) == 7) {
+          p.sk_flags[wi.slot] = 0;
+          p.sk_flags[256 + wi.slot] = 0;
+        }
+      }
 
       if (gnp != nullptr) {
         // One 64-byte record [8 groups][sum, sumsq] per (M tile, sample slot): the eight warps' staging rows are
@@ -844,7 +945,7 @@ static int launch_igemm(const ConvKernelParams& kp, cudaStream_t st) {
     SRGD_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::kTotal));
   }
-  int grid = kp.total_tiles < sm_count() ? kp.total_tiles : sm_count();
+  int grid = kp.total_items < sm_count() ? kp.total_items : sm_count();
   SRGD_CUDA_OK(launch_k(conv_igemm_kernel<BN, STAGES>, dim3(grid), dim3(kThreads), L::kTotal, st, kp));
   count_launch();
   return SRGD_OK;
@@ -873,6 +974,11 @@ extern "C" int srgd_conv_m_tiles(int32_t B, int32_t Ho, int32_t Wo) {
   return g.m_tiles << g.tn_log2;                         // gn_partials records: one per (M tile, sample slot)
 }
 
+extern "C" size_t srgd_conv_splitk_workspace_bytes(void) {
+  // flags (4 KiB) + one 128 x 256 fp32 accumulator per helper part; helpers < CTAs of the grid <= SMs (160 covers B200)
+  return 4096 + (size_t)160 * 128 * 256 * sizeof(float);
+}
+
 extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
@@ -890,9 +996,20 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   const bool swapped = d->Cout % 128 == 0 && d->Cout % 256 != 0 && d->residual == nullptr &&
                        d->out_mode == SRGD_OUT_BF16_NHWC && (d->gn_partials == nullptr || d->Cout / 8 <= 32) &&
                        !(force != nullptr && force[0] == 'n');
-  // pick the N tile: widest that divides Cout, but keep enough tiles to fill the SMs
+  int total_kb_all = 0;
+  for (int i = 0; i < d->n_phase; ++i) total_kb_all += d->srcs[d->phases[i].src].C / kBK;
+  // split-K needs the caller's workspace (flags zeroed once) and is a property of the pixels-as-M kernel
+  const char* sk_env = getenv("SRGD_CONV_SPLITK");         // test knob: "0" = never split
+  // (not in batch-invariant mode: whether a tile is split depends on the launch's tile count, i.e. on the batch, and
+  // a split tile sums its products in another fp32 order)
+  const bool sk_ok = d->splitk_ws != nullptr && !swapped && !(sk_env != nullptr && sk_env[0] == '0') &&
+                     g_batch_invariant == 0 && d->splitk_ws_bytes >= (int64_t)srgd_conv_splitk_workspace_bytes();
+  // pick the N tile: widest that divides Cout, but keep enough tiles to fill the SMs -- with split-K available a
+  // short grid of 256-wide tiles (>= 24 of them, K parts of >= 8 k-blocks) fills the SMs through its K parts
   int BN = 64;
-  if (d->Cout % 256 == 0 && (int64_t)g.m_tiles * (d->Cout / 256) >= sm_count()) BN = 256;
+  const int64_t tiles256 = d->Cout % 256 == 0 ? (int64_t)g.m_tiles * (d->Cout / 256) : 0;
+  if (tiles256 >= sm_count()) BN = 256;
+  else if (sk_ok && tiles256 >= 24 && total_kb_all >= 32) BN = 256;
   else if (d->Cout % 128 == 0) BN = 128;
   if (d->gn_partials) {
     SRGD_REQUIRE(d->Cout % 8 == 0 && (d->Cout / 8) % 8 == 0, "conv: GroupNorm partials need Cout %% 64 == 0");
@@ -975,6 +1092,34 @@ extern "C" int srgd_conv_igemm(const srgd_conv_desc* d, srgd_stream_t stream) {
   kp.m_tiles = g.m_tiles;
   kp.n_tiles = (d->Cout + BN - 1) / BN;
   kp.total_tiles = (swapped ? (kp.m_tiles + 1) / 2 : kp.m_tiles) * kp.n_tiles;
+  {
+    int it = 0;
+    for (int i = 0; i < d->n_phase; ++i) {
+      kp.ph_iter0[i] = (int16_t)it;
+      it += kp.ph_cblocks[i];
+    }
+  }
+  // split-K of the partial last wave (see WorkItem): rem tiles on sm_count CTAs, rem <= sm_count / 2
+  kp.n_full = kp.total_tiles; kp.split = 1; kp.kb_per_part = total_kb; kp.total_items = kp.total_tiles;
+  if (sk_ok) {
+    const int G = sm_count();
+    const int rem = kp.total_tiles % G;
+    int split = rem > 0 ? G / rem : 1;
+    if (split > 4) split = 4;
+    while (split > 1 && total_kb / split < 8) --split;     // parts of at least 8 k-blocks
+    if (split > 1) {
+      int per = (total_kb + split - 1) / split;
+      while (split > 1 && (split - 1) * per >= total_kb) { --split; per = (total_kb + split - 1) / split; }
+      if (split > 1 && rem <= 256) {
+        kp.n_full = kp.total_tiles - rem;
+        kp.split = split;
+        kp.kb_per_part = per;
+        kp.total_items = kp.n_full + rem * split;
+        kp.sk_flags = reinterpret_cast<int32_t*>(d->splitk_ws);
+        kp.sk_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->splitk_ws) + 4096);
+      }
+    }
+  }
   kp.group_size = d->Cout / 8;
   kp.act = d->act; kp.out_mode = d->out_mode;
   kp.bias = d->bias; kp.row_scale = d->row_scale;

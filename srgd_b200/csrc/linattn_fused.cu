@@ -42,6 +42,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
+__device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 
 // ---------------------------------------------------------------------------------------------
 // kernel A: context partials
@@ -268,25 +269,29 @@ __global__ void __launch_bounds__(320, 1) la_ctx_kernel(const __grid_constant__ 
 // GEMM  y = softmax_d(q) Mb^T  instead of  o = softmax_d(q) ctx ; y = o Wout^T  (model.py:322-324).
 // block = (b, h), 128 threads: d = t & 31, quarter t >> 5 of the C output channels.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restrict__ part, const bf16* __restrict__ wout,
-                                                          bf16* __restrict__ mb, int splits, int C) {
-  extern __shared__ uint8_t merge_smem[];                  // Wout[:, h*32:(h+1)*32] as bf16 [C][32] | float [4][34][32]
+constexpr int kMergeWarps = 16;
+__global__ void __launch_bounds__(kMergeWarps * 32) la_merge_mb_kernel(const float* __restrict__ part,
+                                                                      const bf16* __restrict__ wout,
+                                                                      bf16* __restrict__ mb, int splits, int C) {
+  extern __shared__ uint8_t merge_smem[];                  // Wout[:, h*32:(h+1)*32] as bf16 [C][32] | float [16][34][32]
   const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
   const int d = threadIdx.x & 31, cq = threadIdx.x >> 5;
   uint4* wsm = reinterpret_cast<uint4*>(merge_smem);
   float* red = reinterpret_cast<float*>(merge_smem + (size_t)C * 64);
-  for (int i = threadIdx.x; i < C * 4; i += 128)           // 4 x 16 B per output channel
+  for (int i = threadIdx.x; i < C * 4; i += kMergeWarps * 32)   // 4 x 16 B per output channel
     wsm[i] = __ldg(reinterpret_cast<const uint4*>(wout + (int64_t)(i >> 2) * kLfHid + h * 32) + (i & 3));
   pdl_wait();                                             // weights above are never written by a kernel
-  // each warp (cq) folds every fourth split record; the four partial results are combined through shared memory
+  // Each of the 16 warps folds every sixteenth split record (a one-tile launch has 2 x 148 of them per sample: with
+  // four warps this serial chain of L2 round trips was the longest kernel of the block); the sixteen partial results
+  // are combined through shared memory in a fixed order, so the result does not depend on timing.
   const float* base = part + (int64_t)b * splits * (34 * kLfHid) + h * 32 + d;
   const int64_t sstride = 34 * kLfHid;
   float m = -INFINITY;
-  for (int s = cq; s < splits; s += 4) m = fmaxf(m, __ldg(base + s * sstride));
+  for (int s = cq; s < splits; s += kMergeWarps) m = fmaxf(m, __ldg(base + s * sstride));
   float z = 0.f, acc[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-  for (int s = cq; s < splits; s += 4) {
+  for (int s = cq; s < splits; s += kMergeWarps) {
     const float* src = base + s * sstride;
     const float ms = __ldg(src);
     const float w = (ms == -INFINITY) ? 0.f : __expf(ms - m);   // empty records (CTA without tiles) carry m = -inf
@@ -302,12 +307,12 @@ __global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restric
   __syncthreads();
   float mm = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) mm = fmaxf(mm, red[(k * 34) * 32 + d]);
+  for (int k = 0; k < kMergeWarps; ++k) mm = fmaxf(mm, red[(k * 34) * 32 + d]);
   z = 0.f;
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
+#pragma unroll 4
+  for (int k = 0; k < kMergeWarps; ++k) {
     const float* r = red + (k * 34) * 32 + d;
     const float mk = r[0];
     const float w = (mk == -INFINITY) ? 0.f : __expf(mk - mm);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restric
   const float inv = kLfQScale / z;
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] *= inv;
-  const int cper = C >> 2;
+  const int cper = C / kMergeWarps;
 #pragma unroll 2
   for (int c = cq * cper; c < (cq + 1) * cper; ++c) {
     float sum = 0.f;
@@ -331,6 +336,18 @@ __global__ void __launch_bounds__(128) la_merge_mb_kernel(const float* __restric
     }
     mb[((int64_t)b * C + c) * kLfHid + h * 32 + d] = __float2bfloat16(sum);
   }
+}
+
+// host launcher shared with linattn_pp.cu: > 48 KB of dynamic shared memory needs the per-device opt-in
+int launch_la_merge(const float* part, const bf16* wout, bf16* mb, int B, int splits, int C, cudaStream_t st) {
+  const size_t smem = (size_t)C * 64 + (size_t)kMergeWarps * 34 * 32 * 4;
+  static uint64_t configured = 0;
+  if (first_launch_on_device(configured)) {
+    SRGD_CUDA_OK(cudaFuncSetAttribute(la_merge_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      512 * 64 + kMergeWarps * 34 * 32 * 4));
+  }
+  SRGD_CUDA_OK(launch_k(la_merge_mb_kernel, dim3(B * 4), dim3(kMergeWarps * 32), smem, st, part, wout, mb, splits, C));
+  return SRGD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,7 +554,10 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
       const float tot = ssq_t[row] + ssq_t[128 + row];
       const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
       const bf16* xrow = p.x + px * C + c_first;
-      bf16* orow = p.out + px * C + c_first;
+      // Output rows go through this warp's own 4 KB of the softmax(q) operand tile (free once the Y MMA has completed):
+      // 64 columns are written row-wise, then read back so that eight lanes cover one row's 128 bytes -- a store
+      // instruction touches 4 full lines instead of 32 half sectors.
+      const int64_t px0 = (int64_t)(b * p.tiles_per_sample + t0 + it) * 128 + q * 32;
 #pragma unroll 1
       for (int cc = 0; cc < kYChunks; ++cc) {
         uint4 xr[4];
@@ -562,7 +582,19 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
           o[5] = (__uint_as_float(v[jj * 8 + 5]) + b1.y) * scale * g1.y + r[5];
           o[6] = (__uint_as_float(v[jj * 8 + 6]) + b1.z) * scale * g1.z + r[6];
           o[7] = (__uint_as_float(v[jj * 8 + 7]) + b1.w) * scale * g1.w + r[7];
-          st_stream(orow + cc * 32 + jj * 8, pack8(o));
+          const uint4 pk = pack8(o);
+          st_shared_v4(qs_smem + ptx::sw128_offset(row, (cc & 1) * 4 + jj), pk.x, pk.y, pk.z, pk.w);
+        }
+        if (cc & 1) {
+          __syncwarp();
+          const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rl = k * 4 + sub;
+            const uint4 pk = ld_shared_v4(qs_smem + ptx::sw128_offset(q * 32 + rl, chunk));
+            st_stream(p.out + (px0 + rl) * C + c_first + (cc >> 1) * 64 + chunk * 8, pk);
+          }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();
@@ -674,8 +706,8 @@ extern "C" int srgd_linear_attention_block(const void* x, const float* inv_norm,
   }
   SRGD_CUDA_OK(launch_k(la_ctx_kernel, dim3(splits, B), dim3(320), LaCtxSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_kernel");
-  SRGD_CUDA_OK(launch_k(la_merge_mb_kernel, dim3(B * 4), dim3(128), (size_t)C * 64 + 4 * 34 * 32 * 4, st, part,
-                        reinterpret_cast<const bf16*>(out_w), bd, splits, C));
+  rc = launch_la_merge(part, reinterpret_cast<const bf16*>(out_w), bd, B, splits, C, st);
+  if (rc) return rc;
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
   count_launch(2);
 

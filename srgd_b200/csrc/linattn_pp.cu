@@ -358,6 +358,10 @@ struct alignas(64) LaOutPpParams {
   bf16* out;
   int32_t chunks, tiles_per_sample;
 };
+#ifndef SRGD_PP_STAGE
+#define SRGD_PP_STAGE 1
+#endif
+constexpr bool kPpStage = SRGD_PP_STAGE != 0;            // output rows through a shared-memory transpose (A/B knob)
 struct LaOutPpSmem {
   static constexpr int kWqOffset = 0;                         // 2 k-blocks x 16 KB
   static constexpr int kMbOffset = 32768;                     // 2 k-blocks x 16 KB
@@ -553,7 +557,9 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&qs_ready[g]);
 
-      // residual row (L2-hot: the TMA fetched the same lines), requested while the Y MMA runs
+      // residual row (L2-hot: the TMA fetched the same lines), requested while the Y MMA runs.  (Taking it from the x
+      // ring slot instead -- slot handed back by the epilogue -- was tried in round 2: nondeterministic results at
+      // B=16, 128x128, cause not found; profiles/r02_experiments.txt.)
       const bf16* xrow = p.x + px * C + half * 64;
       uint4 xr[8];
 #pragma unroll
@@ -581,7 +587,9 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
       pp_bar_sync(1 + g, 256);
       const float tot = ssq + ptx::lds_f32(ssq_addr + ((half ^ 1) * 128 + row) * 4);
       const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
-      bf16* orow = p.out + px * C + half * 64;
+      // Output rows go through this warp's own 4 KB of the softmax(q) operand tile (free once the Y MMA has
+      // completed): written row-wise, read back so that eight lanes cover one row's 128 bytes -- a store instruction
+      // then touches 4 full lines instead of 32 half sectors.
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {                     // unrolled (xr[] stays in registers); 16 columns at a time
         uint32_t v[16];                                    // keeps the live set under the 96-register cap of 576 threads
@@ -603,12 +611,25 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
           o[5] = fmaf(__uint_as_float(v[jj * 8 + 5]) + b1.y, scale * g1.y, r[5]);
           o[6] = fmaf(__uint_as_float(v[jj * 8 + 6]) + b1.z, scale * g1.z, r[6]);
           o[7] = fmaf(__uint_as_float(v[jj * 8 + 7]) + b1.w, scale * g1.w, r[7]);
-          st_stream(orow + cc * 16 + jj * 8, pack8(o));
+          const uint4 pk = pack8(o);
+          if (kPpStage) ptx::sts_v4(qs_addr + ptx::sw128_offset(row, cc * 2 + jj), pk.x, pk.y, pk.z, pk.w);
+          else st_stream(p.out + px * C + half * 64 + cc * 16 + jj * 8, pk);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&y_done[g]);
+      if (lane == 0) ptx::mbar_arrive(&y_done[g]);         // the accumulator is drained; the copy-out needs no TMEM
+      if (kPpStage) {
+        const int64_t px0 = row0 + (int64_t)(2 * it + g) * 128 + q * 32;
+        const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rl = k * 4 + sub;                      // row of this warp's 32
+          const uint4 pk = ptx::lds_v4(qs_addr + ptx::sw128_offset(q * 32 + rl, chunk));
+          st_stream(p.out + (px0 + rl) * C + half * 64 + chunk * 8, pk);
+        }
+        __syncwarp();                                      // the tile is rewritten by the next softmax
+      }
     }
   }
 
@@ -621,8 +642,7 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
 }
 
 // merge kernel of linattn_fused.cu
-__global__ void la_merge_mb_kernel(const float* __restrict__ part, const bf16* __restrict__ wout, bf16* __restrict__ mb,
-                                   int splits, int C);
+int launch_la_merge(const float* part, const bf16* wout, bf16* mb, int B, int splits, int C, cudaStream_t st);
 
 // Launches the C = 128 ping-pong pipeline: context partials -> merge -> output.  `inv` = 1/||x|| per pixel.
 int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, const float* out_b, const float* out_g,
@@ -643,8 +663,8 @@ int launch_la_block_pp(const void* x, const void* qkv_w, const void* out_w, cons
   }
   SRGD_CUDA_OK(launch_k(la_ctx_pp_kernel, dim3(splits, B), dim3(576), LaCtxPpSmem::kTotal, st, ap));
   SRGD_LAUNCH_OK("la_ctx_pp_kernel");
-  SRGD_CUDA_OK(launch_k(la_merge_mb_kernel, dim3(B * 4), dim3(128), (size_t)(128 * 64 + 4 * 34 * 32 * 4), st, part,
-                        reinterpret_cast<const bf16*>(out_w), bd, 2 * splits, 128));
+  rc = launch_la_merge(part, reinterpret_cast<const bf16*>(out_w), bd, B, 2 * splits, 128, st);
+  if (rc) return rc;
   SRGD_LAUNCH_OK("la_merge_mb_kernel");
 
   LaOutPpParams bp;

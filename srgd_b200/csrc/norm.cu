@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 // REG: C/8 is a power of two <= 256, so a thread always meets the same 8 channels (every stride is a multiple of
 // 256 vectors) and keeps its affine coefficients -- and the final-conv weights -- in registers: no shared-memory
 // traffic and no block barrier.
+// FINAL keeps 24 final-conv weights in registers next to the 16 affine coefficients: under the 64-register cap of
+// 4 CTAs per SM it spilled (72 B of stores / 132 B of loads per thread, ptxas -v), so that instance runs 3 CTAs per SM.
 template <bool HAS_RES, int INV_LANES, bool FINAL, bool REG, int U>
-__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, FINAL ? 3 : 4) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
@@ -149,7 +151,9 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx,
   bf16* ys = y + (int64_t)b * HW * C;
   // U independent 16-byte vectors (2U with a residual) in flight per thread per iteration; the first batch is
   // issued BEFORE the affine coefficients are loaded, so a CTA pays one memory latency, not two, before its
-  // first store.  U = 2 is the measured optimum: U = 4 costs occupancy (90 registers) and was 11 % slower.
+  // first store.  Four loads in flight per thread is the measured optimum: U = 2 with a residual (U = 4 there costs
+  // occupancy, 90 registers, and was 11 % slower), U = 4 without one (the plain pass at U = 2 moved 4.6 TB/s where
+  // the residual pass moved 5.7 TB/s).
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint4 xv[U], rv[U];
@@ -431,7 +435,7 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
   const int vpp = C / 8;
   const bool reg = (vpp & (vpp - 1)) == 0 && vpp <= 256;
 #define SRGD_GN_LAUNCH(RES, INV, R)                                                                              \
-  SRGD_CUDA_OK(launch_k(gn_apply_kernel<RES, INV, false, R, 2>, grid, dim3(256), R ? 0 : smem, cst, xr, Bx,       \
+  SRGD_CUDA_OK(launch_k(gn_apply_kernel<RES, INV, false, R, RES ? 2 : 4>, grid, dim3(256), R ? 0 : smem, cst, xr, Bx, \
                         stats, gamma, beta, scale_shift, ss_stride, rr, yr, inv_out, nullptr, nullptr, nullptr,   \
                         H * W, C, gn_reverse(), gn_partials, geom))
   if (inv_out != nullptr && C == 128) SRGD_GN_LAUNCH(true, 16, true);
@@ -460,7 +464,7 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
                "groupnorm_apply_final: needs C == 128 and an even pixel count (B=%d H=%d W=%d C=%d)", B, H, W, C);
   const int64_t total = (int64_t)H * W * (C / 8);
   int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
-  const int cap = sm_count() * gn_ctas_per_sm();
+  const int cap = sm_count() * (gn_ctas_per_sm() < 3 ? gn_ctas_per_sm() : 3);     // this instance: 3 CTAs per SM
   if ((int64_t)gx * B > cap) gx = (cap + B - 1) / B;
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 5 * sizeof(float);

@@ -241,6 +241,8 @@ struct Fwd {
   int B;
   int rc = SRGD_OK;
   const float* ss = nullptr;       // [B][ss_total] scale/shift for all ResnetBlocks
+  void* sk_ws = nullptr;           // split-K workspace shared by every conv launch of the forward (conv_igemm.cu)
+  int64_t sk_bytes = 0;
 
   bool ok() const { return rc == SRGD_OK; }
   void run(int r) {
@@ -287,6 +289,7 @@ struct Fwd {
     d.weight = w; d.Ktot = (int64_t)ksize * ksize * ctot;
     d.bias = bias; d.row_scale = row_scale; d.residual = residual; d.act = act; d.out_mode = out_mode; d.out = out;
     d.gn_partials = (conv_impl & 3) ? nullptr : partials;
+    d.splitk_ws = sk_ws; d.splitk_ws_bytes = sk_bytes;
     run((conv_impl & 1) ? srgd_conv_direct(&d, st) : srgd_conv_igemm(&d, st));
   }
 
@@ -419,6 +422,7 @@ struct Fwd {
         d.phases[i] = {i, 0, 0, i * cin};
       }
       d.weight = c.w; d.Ktot = c.cin; d.bias = c.b; d.out = out; d.out_mode = SRGD_OUT_BF16_NHWC;
+      d.splitk_ws = sk_ws; d.splitk_ws_bytes = sk_bytes;
       run((conv_impl & 1) ? srgd_conv_direct(&d, st) : srgd_conv_igemm(&d, st));
     }
     tap(c.name, out, (size_t)B * Ho * Wo * c.cout * 2);
@@ -434,6 +438,14 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   const int n = c.n_stages;
   const int dim = c.dim, td = u.time_dim;
   const size_t M0 = (size_t)B * H * W;
+
+  // ---- split-K workspace of the conv launches: flags zeroed once per forward (the kernels re-arm them) ----
+  f.sk_bytes = (int64_t)srgd_conv_splitk_workspace_bytes();
+  f.sk_ws = f.alloc((size_t)f.sk_bytes);
+  if (!dry && f.ok()) {
+    cudaError_t e = cudaMemsetAsync(f.sk_ws, 0, 4096, as_stream(st));
+    if (e != cudaSuccess) f.run(fail_cuda(e, "split-K flag reset"));
+  }
 
   // ---- embeddings (model.py:689-694 and every ResnetBlock.mlp, 264-267/277-279) ----
   const int fdim = c.sinu_dim + 1;
@@ -545,6 +557,7 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   }
   ar.release(t);
   ar.release(ss);
+  ar.release(f.sk_ws);
   return f.rc;
 }
 

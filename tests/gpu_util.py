@@ -39,8 +39,14 @@ def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).float()
 
 
+def splitk_workspace():
+    """A split-K workspace for srgd_conv_desc.splitk_ws (flags zeroed once; the kernels re-arm them)."""
+    n = _lib.load().srgd_conv_splitk_workspace_bytes()
+    return torch.zeros(n, dtype=torch.uint8, device="cuda")
+
+
 def conv_desc(srcs, phases, weight, Ktot, B, Ho, Wo, Cout, out, bias=None, row_scale=None, residual=None, act=0,
-              out_mode=0, gn_partials=None):
+              out_mode=0, gn_partials=None, splitk_ws=None):
     """srcs: list of (tensor_or_ptr, sb, sy, sx, H, W, C); phases: list of (src, dy, dx, k_start)."""
     d = _lib.ConvDesc()
     d.B, d.Ho, d.Wo, d.Cout = B, Ho, Wo, Cout
@@ -58,7 +64,9 @@ def conv_desc(srcs, phases, weight, Ktot, B, Ho, Wo, Cout, out, bias=None, row_s
     d.act, d.out_mode = act, out_mode
     d.out = out.data_ptr()
     d.gn_partials = gn_partials.data_ptr() if gn_partials is not None else None
-    d._keep = [srcs, weight, out, bias, row_scale, residual, gn_partials]     # keep the storages alive
+    d.splitk_ws = splitk_ws.data_ptr() if splitk_ws is not None else None
+    d.splitk_ws_bytes = splitk_ws.numel() if splitk_ws is not None else 0
+    d._keep = [srcs, weight, out, bias, row_scale, residual, gn_partials, splitk_ws]     # keep the storages alive
     return d
 
 
