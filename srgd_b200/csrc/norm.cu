@@ -120,10 +120,11 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 // REG: C/8 is a power of two <= 256, so a thread always meets the same 8 channels (every stride is a multiple of
 // 256 vectors) and keeps its affine coefficients -- and the final-conv weights -- in registers: no shared-memory
 // traffic and no block barrier.
-// FINAL keeps 24 final-conv weights in registers next to the 16 affine coefficients: under the 64-register cap of
-// 4 CTAs per SM it spilled (72 B of stores / 132 B of loads per thread, ptxas -v), so that instance runs 3 CTAs per SM.
+// (FINAL keeps 24 final-conv weights in registers next to the 16 affine coefficients and spills 72 B per thread under
+// the 64-register cap of 4 CTAs per SM; 3 CTAs per SM without spills was measured SLOWER, 0.30 vs 0.24 ms at 16
+// tiles -- the pass is bound by loads in flight per SM, not by the spill traffic; profiles/r02_experiments.txt.)
 template <bool HAS_RES, int INV_LANES, bool FINAL, bool REG, int U>
-__global__ void __launch_bounds__(256, FINAL ? 3 : 4) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
@@ -464,7 +465,7 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
                "groupnorm_apply_final: needs C == 128 and an even pixel count (B=%d H=%d W=%d C=%d)", B, H, W, C);
   const int64_t total = (int64_t)H * W * (C / 8);
   int gx = stream_grid((total + 256 * 4 - 1) / (256 * 4), 8);
-  const int cap = sm_count() * (gn_ctas_per_sm() < 3 ? gn_ctas_per_sm() : 3);     // this instance: 3 CTAs per SM
+  const int cap = sm_count() * gn_ctas_per_sm();
   if ((int64_t)gx * B > cap) gx = (cap + B - 1) / B;
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 5 * sizeof(float);
