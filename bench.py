@@ -340,7 +340,7 @@ class TiledWorkload:
         import torch.nn.functional as F
         from srgd_b200.tiled import CudaTiledOps
         from srgd_b200.tiling import TilePlan
-        self.diff, self.dev, self.ccs, self.shard = diff, dev, ccs, shard
+        self.diff, self.dev, self.ccs, self.shard, self.rank = diff, dev, ccs, shard, rank
         self.images = images
         first = 0 if shard else rank * images                 # sharded: every rank holds the same image
         cond = synth_inputs(images, first=first, lr_size=lr) * 2 - 1
@@ -383,21 +383,37 @@ class TiledWorkload:
         return self.diff._finalize(self.img[:, :, t:b, l:r].contiguous())
 
     def run_e2e(self, first, count):
+        """Per step: state canvas and condition canvas host -> device (every rank needs them), one sampling step, next
+        canvas device -> host.  The result is replicated in the tile-sharded workload, so rank 0 alone reads it back;
+        the read-back runs on a second stream from a staging copy and overlaps the next step."""
         if self._host is None:
             self._host = dict(x=self.img.cpu().pin_memory(), c=self.cond_canvas.cpu().pin_memory(),
-                              r=torch.empty(self.img.shape).pin_memory())
+                              r=torch.empty(self.img.shape).pin_memory(), stage=torch.empty_like(self.img),
+                              copy=torch.cuda.Stream(device=self.dev), staged=torch.cuda.Event(),
+                              done=torch.cuda.Event())
         h = self._host
-        cur = torch.cuda.current_stream()
+        cur, cp = torch.cuda.current_stream(), h["copy"]
+        reads_back = (not self.shard) or self.rank == 0
+        h["done"].record(cp)
         for k in range(count):
             self.img.copy_(h["x"], non_blocking=True)
             self.cond_canvas.copy_(h["c"], non_blocking=True)
             self._steps(first + k, 1)
-            h["r"].copy_(self.img, non_blocking=True)
-            cur.synchronize()
+            if reads_back:
+                cur.wait_event(h["done"])                      # the previous read-back has left the staging canvas
+                h["stage"].copy_(self.img)
+                h["staged"].record(cur)
+                with torch.cuda.stream(cp):
+                    cp.wait_event(h["staged"])
+                    h["r"].copy_(h["stage"], non_blocking=True)
+                    h["done"].record(cp)
+        h["done"].synchronize()
+        cur.wait_stream(cp)
+        cur.synchronize()
 
     e2e_call = ("one sampling step of tiled_sample()'s loop (srgd_b200.tiled.run_tiled) per call with the pinned host "
-                "state canvas and condition canvas copied in and the next canvas copied out, every step; copy in, "
-                "step, copy out, sync")
+                "state canvas and condition canvas copied in (every rank) and the next canvas copied out (rank 0 in the "
+                "tile-sharded workload: the result is replicated), every step; the read-back overlaps the next step")
 
 
 def main():
@@ -554,6 +570,23 @@ def main():
                     for i, (kind, ms, fl, by) in enumerate(recs[-per:]):
                         f.write(f"{i} {kind} {ms:.4f} {fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f} "
                                 f"{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.0f}\n")
+        # ---- the exchange step of the tile-sharded workload, timed alone: one all_gather_into_tensor of the largest
+        # per-rank tile stack (what run_tiled issues once per step), CUDA events, max over ranks ----
+        exchange = None
+        if w.get("shard") and world > 1:
+            from srgd_b200.sharding import shard_range
+            n_even = len(wl.plan.grids[0])
+            width = max(hi - lo for lo, hi in (shard_range(n_even, world, r) for r in range(world)))
+            send = torch.zeros(images, width, 3, TILE, TILE, device=dev)
+            recv = torch.empty((world,) + tuple(send.shape), device=dev)
+            for _ in range(3):
+                dist.all_gather_into_tensor(recv.flatten(0, 1), send)
+            ex_ms = max_over_ranks(timed(lambda: [dist.all_gather_into_tensor(recv.flatten(0, 1), send)
+                                                  for _ in range(20)])) / 20
+            exchange = dict(collective="all_gather_into_tensor (NCCL), once per sampling step",
+                            bytes_per_rank=send.numel() * 4, bytes_gathered=recv.numel() * 4, ms_standalone=ex_ms,
+                            note="issued asynchronously; the odd steps' full-canvas noise draw overlaps it")
+            del send, recv
         eager = None
         if rank == 0 and world == 1 and not args.no_gpu_eager:
             del wl
@@ -644,6 +677,9 @@ def main():
         kernel_ms_per_step={k: round(v["ms"], 4) for k, v in prof.items()},
         clocks=clocks,
     )
+    if exchange is not None:
+        exchange["share_of_step"] = exchange["ms_standalone"] / ms_per_step
+        line["exchange"] = exchange
     if w["kind"] == "sweep":
         line["sweep"] = sweep
     if eager is not None:
