@@ -174,6 +174,14 @@ int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stats, const fl
                          const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
                          int32_t C, srgd_stream_t stream);
 
+/* The same with a broadcast residual: row b adds row (b % res_rows) of `residual` (B a multiple of res_rows).  Used
+ * when the two halves of a class-guidance batch share init_conv's output as the identity residual of the first
+ * ResnetBlock (model.py:3151-3154 run the same x twice; here it is computed once). */
+int srgd_groupnorm_apply_ex(const void* x, int32_t Bx, const float* stats, const float* gn_partials,
+                            const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
+                            const void* residual, int32_t res_rows, void* y, float* inv_out, int32_t B, int32_t H,
+                            int32_t W, int32_t C, srgd_stream_t stream);
+
 /* Last ResnetBlock of the network fused with the final 1x1 conv (model.py:674-675, 724-725):
  * eps[b][o][y][x] = final_b[o] + sum_c final_w[o][c] * ( SiLU(GN(x)*gamma+beta) + residual )[b][y][x][c],
  * fp32 NCHW out, o < 3; the normalised activation itself is never stored.  C must be 128. */

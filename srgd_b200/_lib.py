@@ -83,6 +83,7 @@ SIGNATURES = {
     "srgd_groupnorm_finalize": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_groupnorm_stats": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_groupnorm_apply": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "srgd_groupnorm_apply_ex": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_groupnorm_apply_final": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "srgd_pixel_inv_norm": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "srgd_rmsnorm_residual": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx,
                                                        const bf16* residual, bf16* y, float* __restrict__ inv_out,
                                                        const float* __restrict__ fin_w, const float* __restrict__ fin_b,
                                                        float* __restrict__ eps, int HW, int C, int reverse,
-                                                       const float* __restrict__ partials, TileGeom geom) {
+                                                       const float* __restrict__ partials, TileGeom geom, int Bres) {
   extern __shared__ float sm[];                          // !REG: A[C] | B[C] | (FINAL: fin_w[3][C])
   __shared__ double red[8][4][4];
   __shared__ float st16[16];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const bf16* x, int Bx,
   const int vec_per_pix = C / 8;
   const int64_t total = (int64_t)HW * vec_per_pix;
   const bf16* xs = x + (int64_t)bs * HW * C;
-  const bf16* rs = HAS_RES ? residual + (int64_t)b * HW * C : nullptr;
+  const bf16* rs = HAS_RES ? residual + (int64_t)(b % Bres) * HW * C : nullptr;   // broadcast residual: Bres rows
   bf16* ys = y + (int64_t)b * HW * C;
   // U independent 16-byte vectors (2U with a residual) in flight per thread per iteration; the first batch is
   // issued BEFORE the affine coefficients are loaded, so a CTA pays one memory latency, not two, before its
@@ -410,8 +410,20 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
                                     const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                                     const void* residual, void* y, float* inv_out, int32_t B, int32_t H, int32_t W,
                                     int32_t C, srgd_stream_t stream) {
+  return srgd_groupnorm_apply_ex(x, Bx, stats, gn_partials, gamma, beta, scale_shift, ss_stride, residual, B, y, inv_out,
+                                 B, H, W, C, stream);
+}
+
+extern "C" int srgd_groupnorm_apply_ex(const void* x, int32_t Bx, const float* stats, const float* gn_partials,
+                                       const float* gamma, const float* beta, const float* scale_shift,
+                                       int64_t ss_stride, const void* residual, int32_t res_rows, void* y,
+                                       float* inv_out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                       srgd_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
+  SRGD_REQUIRE(residual == nullptr || (res_rows > 0 && res_rows <= B && B % res_rows == 0),
+               "groupnorm_apply: B=%d must be a multiple of the residual's rows (%d)", B, res_rows);
+  if (residual == nullptr) res_rows = 1;
   SRGD_REQUIRE(x && gamma && beta && y, "groupnorm_apply: null argument");
   SRGD_REQUIRE((stats != nullptr) != (gn_partials != nullptr),
                "groupnorm_apply: pass exactly one of stats / gn_partials");
@@ -438,7 +450,7 @@ extern "C" int srgd_groupnorm_apply(const void* x, int32_t Bx, const float* stat
 #define SRGD_GN_LAUNCH(RES, INV, R)                                                                              \
   SRGD_CUDA_OK(launch_k(gn_apply_kernel<RES, INV, false, R, RES ? 2 : 4>, grid, dim3(256), R ? 0 : smem, cst, xr, Bx, \
                         stats, gamma, beta, scale_shift, ss_stride, rr, yr, inv_out, nullptr, nullptr, nullptr,   \
-                        H * W, C, gn_reverse(), gn_partials, geom))
+                        H * W, C, gn_reverse(), gn_partials, geom, res_rows))
   if (inv_out != nullptr && C == 128) SRGD_GN_LAUNCH(true, 16, true);
   else if (inv_out != nullptr) SRGD_GN_LAUNCH(true, 32, true);
   else if (residual && reg) SRGD_GN_LAUNCH(true, 0, true);
@@ -474,7 +486,7 @@ extern "C" int srgd_groupnorm_apply_final(const void* x, const float* stats, con
   SRGD_CUDA_OK(launch_k(gn_apply_kernel<true, 0, true, true, 2>, grid, dim3(256), 0, as_stream(stream),
                         reinterpret_cast<const bf16*>(x), B, stats, gamma, beta, nullptr, 0,
                         reinterpret_cast<const bf16*>(residual), nullptr, nullptr, final_w, final_b, eps, H * W, C,
-                        gn_reverse(), gn_partials, geom));
+                        gn_reverse(), gn_partials, geom, B));
   count_launch();
   return SRGD_OK;
 }

@@ -3,6 +3,7 @@
 // workspace.  No allocation, no synchronisation: buffer addresses come from a deterministic
 // first-fit arena over the workspace, so the same (B,H,W) always yields the same launch sequence
 // with the same pointers (CUDA-graph friendly).
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -267,12 +268,14 @@ struct Fwd {
   }
 
   // generic conv over up to two concatenated NHWC sources with a kxk window
+  // `rows` < 0: all B rows; otherwise a launch over `rows` samples (a group of a broadcast-batch consumer)
   void conv(const void* a0, int c0, const void* a1, int c1, int H, int W, int ksize, const void* w, const float* bias,
-            int cout, void* out, float* partials, const float* row_scale, const void* residual, int act, int out_mode) {
+            int cout, void* out, float* partials, const float* row_scale, const void* residual, int act, int out_mode,
+            int rows = -1) {
     if (dry || !ok()) return;
     srgd_conv_desc d;
     memset(&d, 0, sizeof(d));
-    d.B = B; d.Ho = H; d.Wo = W; d.Cout = cout;
+    d.B = rows < 0 ? B : rows; d.Ho = H; d.Wo = W; d.Cout = cout;
     d.n_src = a1 ? 2 : 1;
     d.srcs[0] = {a0, (int64_t)H * W * c0, (int64_t)W * c0, (int64_t)c0, H, W, c0};
     if (a1) d.srcs[1] = {a1, (int64_t)H * W * c1, (int64_t)W * c1, (int64_t)c1, H, W, c1};
@@ -300,25 +303,57 @@ struct Fwd {
     if (!dry && ok() && (conv_impl & 3)) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
   }
 
+  // A conv whose second source has only Bb < B rows (the same rows for every group of Bb samples: init_conv's output
+  // shared by the two halves of a class-guidance batch): B / Bb launches over Bb samples each.  The GroupNorm partial
+  // records of the groups are laid out as one B-row launch would write them (one record set per sample; H*W >= 128).
+  void conv_bcast(const void* a0, int c0, const void* a1, int c1, int Bb, int H, int W, int ksize, const void* w,
+                  const float* bias, int cout, void* out, float* part) {
+    const size_t px = (size_t)Bb * H * W;
+    const size_t rec = (size_t)srgd_conv_m_tiles(Bb, H, W) * 16;
+    for (int g = 0; g < B / Bb; ++g)
+      conv(reinterpret_cast<const uint8_t*>(a0) + g * px * c0 * 2, c0, a1, c1, H, W, ksize, w, bias, cout,
+           reinterpret_cast<uint8_t*>(out) + g * px * cout * 2, part ? part + g * rec : nullptr, nullptr, nullptr, 0,
+           SRGD_OUT_BF16_NHWC, Bb);
+  }
+
   // ResnetBlock (model.py:261-285).  Consumes nothing; returns a fresh [B][H][W][cout] buffer.
   // inv_out (optional): receives 1/||row|| of the block output for the attention block that follows.
   // eps_out (optional, last block of the network only): the final 1x1 conv is fused into the second GroupNorm pass
   // (srgd_groupnorm_apply_final); the block output is then not materialised and nullptr is returned.
   // GroupNorm statistics never get a launch of their own on the product path: the conv epilogue writes one
   // 64-byte partial record per 128-pixel tile and every block of the apply kernel folds its sample's records.
+  // Class-guidance sharing (Ba / Bb, both default to "all B rows"):
+  //   Ba < B: xa has only Ba rows, the same for every group of Ba samples (the first block of the network on the
+  //           shared init_conv output): conv1 and its GroupNorm statistics are computed once per group member, the
+  //           apply pass broadcasts them to the B rows (whose scale / shift differ), the identity residual is
+  //           broadcast too.  Needs a single source and no res_conv.
+  //   Bb < B: xb has only Bb rows (the final block's concat with init_conv's output): its consumers run as B / Bb
+  //           launches (conv_bcast).
   void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr,
-                 float* eps_out = nullptr) {
+                 float* eps_out = nullptr, int Ba = -1, int Bb = -1) {
     const size_t M = (size_t)B * H * W;
     const bool fused_stats = !(conv_impl & 3);
+    const bool shared_in = Ba > 0 && Ba < B, bcast_b = Bb > 0 && Bb < B;
     void* c1 = alloc(M * r.cout * 2);
     float* stats = reinterpret_cast<float*>(alloc((size_t)B * 8 * 2 * sizeof(float)));
     float* part = reinterpret_cast<float*>(alloc((size_t)srgd_conv_m_tiles(B, H, W) * 8 * 2 * sizeof(float)));
     const float* st_arg = fused_stats ? nullptr : stats;
     const float* pt_arg = fused_stats ? part : nullptr;
-    conv_gn(xa, r.cin0, xb, r.cin1, H, W, r.c1_w, r.c1_b, r.cout, c1, part, stats);
-    if (!dry && ok())
-      run(srgd_groupnorm_apply(c1, B, st_arg, pt_arg, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, nullptr,
-                               B, H, W, r.cout, st));
+    if (shared_in) {
+      void* c1s = alloc((size_t)Ba * H * W * r.cout * 2);
+      conv(xa, r.cin0, nullptr, 0, H, W, 3, r.c1_w, r.c1_b, r.cout, c1s, part, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC,
+           Ba);
+      if (!dry && ok())
+        run(srgd_groupnorm_apply(c1s, Ba, nullptr, part, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1,
+                                 nullptr, B, H, W, r.cout, st));
+      ar.release(c1s);
+    } else {
+      if (bcast_b) conv_bcast(xa, r.cin0, xb, r.cin1, Bb, H, W, 3, r.c1_w, r.c1_b, r.cout, c1, part);
+      else conv_gn(xa, r.cin0, xb, r.cin1, H, W, r.c1_w, r.c1_b, r.cout, c1, part, stats);
+      if (!dry && ok())
+        run(srgd_groupnorm_apply(c1, B, st_arg, pt_arg, r.n1_g, r.n1_b, ss + r.ss_off, u.ss_total, nullptr, c1, nullptr,
+                                 B, H, W, r.cout, st));
+    }
     void* c2 = alloc(M * r.cout * 2);
     conv_gn(c1, r.cout, nullptr, 0, H, W, r.c2_w, r.c2_b, r.cout, c2, part, stats);
     ar.release(c1);
@@ -326,8 +361,10 @@ struct Fwd {
     void* rbuf = nullptr;
     if (r.res_w != nullptr) {                                           // res_conv 1x1 (model.py:271)
       rbuf = alloc(M * r.cout * 2);
-      conv(xa, r.cin0, xb, r.cin1, H, W, 1, r.res_w, r.res_b, r.cout, rbuf, nullptr, nullptr, nullptr, 0,
-           SRGD_OUT_BF16_NHWC);
+      if (bcast_b) conv_bcast(xa, r.cin0, xb, r.cin1, Bb, H, W, 1, r.res_w, r.res_b, r.cout, rbuf, nullptr);
+      else
+        conv(xa, r.cin0, xb, r.cin1, H, W, 1, r.res_w, r.res_b, r.cout, rbuf, nullptr, nullptr, nullptr, 0,
+             SRGD_OUT_BF16_NHWC);
       resid = rbuf;
     }
     if (eps_out != nullptr) {
@@ -341,8 +378,8 @@ struct Fwd {
       return nullptr;
     }
     if (!dry && ok())
-      run(srgd_groupnorm_apply(c2, B, st_arg, pt_arg, r.n2_g, r.n2_b, nullptr, 0, resid, c2, inv_out, B, H, W, r.cout,
-                               st));
+      run(srgd_groupnorm_apply_ex(c2, B, st_arg, pt_arg, r.n2_g, r.n2_b, nullptr, 0, resid,
+                                  (shared_in && rbuf == nullptr) ? Ba : B, c2, inv_out, B, H, W, r.cout, st));
     ar.release(rbuf);
     ar.release(part);
     ar.release(stats);
@@ -466,14 +503,24 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   ar.release(feats);
   ar.release(t1);
 
+  // ---- class guidance: rows b and b + Bx read the same x and the same condition (model.py:3151-3154 runs the U-Net
+  // twice on them) and differ only in the embedding, which first enters at the first block's scale / shift: the input
+  // pack, init_conv and the first conv3x3 + its GroupNorm statistics are computed for Bx rows and broadcast ----
+  const char* share_knob = getenv("SRGD_CFG_SHARE");                   // test knob: "0" = compute both halves in full
+  const bool share_env = !(share_knob != nullptr && share_knob[0] == '0');
+  const bool share = share_env && B == 2 * Bx && (n_cond_rows == B || n_cond_rows == 0) && !(conv_impl & 3) &&
+                     tile_geom(1, H, W).tn_log2 == 0 && u.downs[0].r0.res_w == nullptr;
+  const int Bs = share ? Bx : B;
+  const size_t M0s = (size_t)Bs * H * W;
+
   // ---- init conv 7x7 (model.py:686): row-im2col pack + 7 vertical taps of 64 channels ----
-  void* pk = f.alloc(M0 * 64 * 2);
-  if (!dry && f.ok()) f.run(srgd_pack_input(x, cond, n_cond_rows, Bx, pk, B, H, W, st));
-  void* r = f.alloc(M0 * dim * 2);
+  void* pk = f.alloc(M0s * 64 * 2);
+  if (!dry && f.ok()) f.run(srgd_pack_input(x, cond, share ? (n_cond_rows ? Bs : 0) : n_cond_rows, Bx, pk, Bs, H, W, st));
+  void* r = f.alloc(M0s * dim * 2);
   if (!dry && f.ok()) {
     srgd_conv_desc d;
     memset(&d, 0, sizeof(d));
-    d.B = B; d.Ho = H; d.Wo = W; d.Cout = dim;
+    d.B = Bs; d.Ho = H; d.Wo = W; d.Cout = dim;
     d.n_src = 1; d.n_phase = 7;
     d.srcs[0] = {pk, (int64_t)H * W * 64, (int64_t)W * 64, 64, H, W, 64};
     for (int i = 0; i < 7; ++i) d.phases[i] = {0, i - 3, 0, i * 64};
@@ -481,7 +528,7 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
     f.run((conv_impl & 1) ? srgd_conv_direct(&d, st) : srgd_conv_igemm(&d, st));
   }
   ar.release(pk);
-  f.tap("init_conv", r, M0 * dim * 2);
+  f.tap("init_conv", r, M0s * dim * 2);
 
   // ---- down path (model.py:698-706) ----
   std::vector<void*> skips;
@@ -490,7 +537,7 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   int h = H, w = W;
   for (int i = 0; i < n; ++i) {
     const Stage& s = u.downs[i];
-    void* a = f.resblock(s.r0, xcur, nullptr, h, w);
+    void* a = f.resblock(s.r0, xcur, nullptr, h, w, nullptr, nullptr, (i == 0 && share) ? Bs : -1);
     if (xcur != r) ar.release(xcur);
     skips.push_back(a); skip_c.push_back(s.r0.cout);
     float* inv = f.wants_inv(s.attn, h, w) ? reinterpret_cast<float*>(f.alloc((size_t)B * h * w * sizeof(float))) : nullptr;
@@ -548,7 +595,8 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   }
   // ---- head (model.py:722-725) ----
   const bool fuse_final = !(conv_impl & 1) && u.taps.empty() && dim == 128 && c.channels == 3 && (h * w) % 2 == 0;
-  void* fr = f.resblock(u.final_res, xcur, r, h, w, nullptr, fuse_final ? (dry ? reinterpret_cast<float*>(1) : eps) : nullptr);
+  void* fr = f.resblock(u.final_res, xcur, r, h, w, nullptr, fuse_final ? (dry ? reinterpret_cast<float*>(1) : eps) : nullptr,
+                        -1, share ? Bs : -1);
   ar.release(xcur);
   ar.release(r);
   if (!fuse_final) {
@@ -627,12 +675,13 @@ extern "C" size_t srgd_unet_workspace_bytes(const srgd_unet* u, int32_t B, int32
   if (check_shape(u, B, H, W) != SRGD_OK) return 0;
   // the product plan and the debug plan (conv_impl bit 0: unfused attention) differ: size for both
   size_t need = 0;
-  for (int impl = 0; impl < 2; ++impl) {
-    Arena ar(nullptr, (size_t)1 << 60);
-    forward_impl(*const_cast<srgd_unet*>(u), ar, true, nullptr, nullptr, nullptr, nullptr, 0, B, nullptr, B, H, W, impl,
-                 nullptr);
-    if (ar.high_water() > need) need = ar.high_water();
-  }
+  for (int impl = 0; impl < 2; ++impl)
+    for (int shared = 0; shared < ((B % 2 == 0) ? 2 : 1); ++shared) {       // plain plan and class-guidance sharing plan
+      Arena ar(nullptr, (size_t)1 << 60);
+      forward_impl(*const_cast<srgd_unet*>(u), ar, true, nullptr, nullptr, nullptr, nullptr, shared ? B : 0,
+                   shared ? B / 2 : B, nullptr, B, H, W, impl, nullptr);
+      if (ar.high_water() > need) need = ar.high_water();
+    }
   return need + 256;
 }
 

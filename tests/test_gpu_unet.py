@@ -271,3 +271,33 @@ def test_reload_through_the_diffusion_wrapper_repacks_the_device_weights():
         diff.model.final_conv.bias.add_(0.5)
     c = diff.model(x, lsnr, None, None)
     assert float((c - b - 0.5).abs().max()) < 1e-5
+
+
+def test_class_guidance_sharing_is_bit_identical_to_the_full_batch(monkeypatch):
+    """Class guidance runs rows b and b + B on the same x and condition (model.py:3151-3154): the input pack, init_conv
+    and the first conv3x3 + GroupNorm statistics are computed once and broadcast (unet.cu `share`).  Every broadcast value
+    is the value the full 2B-row launch computes for both rows, so the result must not change by a bit."""
+    diff, sd, spec = build("full", image_size=256)
+    g = torch.Generator().manual_seed(8)
+    B = 3
+    x = torch.randn(B, 3, 256, 256, generator=g).cuda()
+    cond = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    noise = torch.randn(B, 3, 256, 256, generator=g).cuda()
+    label = torch.tensor([1]).cuda()
+    steps = torch.linspace(1., 0., 251)
+    outs = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("SRGD_CFG_SHARE", knob)
+        outs[knob] = diff.p_sample(x, steps[40], cond, label, 1.0, 3.0, steps[41], noise=noise)
+        n_launch = diff.last_step_launches
+        outs[knob + "n"] = n_launch
+    assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][1], outs["0"][1])
+    assert outs["1n"] == outs["0n"] + 2          # the final block's two convs over [x, r] run as two launches each
+    # without a condition (n_cond_rows == 0) the halves share as well; LR-condition guidance (null rows drop the
+    # condition) must NOT share
+    for cs, ccs, c in ((1.0, 3.0, None), (2.0, 1.0, cond)):
+        res = {}
+        for knob in ("1", "0"):
+            monkeypatch.setenv("SRGD_CFG_SHARE", knob)
+            res[knob] = diff.p_sample(x, steps[40], c, label, cs, ccs, steps[41], noise=noise)[0]
+        assert torch.equal(res["1"], res["0"])
