@@ -561,6 +561,7 @@ def main():
             prof = {k: dict(v, ms=v["ms"] / prof_steps, launches=v["launches"] / prof_steps,
                             flops=v["flops"] / prof_steps, bytes=v["bytes"] / prof_steps)
                     for k, v in _lib.profile_report().items()}
+            recs_all = _lib.profile_records() if rank == 0 else []
             if args.dump_launches and rank == 0:
                 recs = _lib.profile_records()
                 per = len(recs) // prof_steps
@@ -655,6 +656,12 @@ def main():
             gbs = prof[k]["bytes"] / (prof[k]["ms"] * 1e-3) / 1e9
             hbm[k] = dict(ms_per_step=prof[k]["ms"], gb_per_s=gbs, frac_of_hbm_peak=gbs / pk["hbm_gbs"],
                           launches_per_step=prof[k]["launches"])
+            # the same over the launches that move more than the 126 MB L2 holds (the others are latency-bound)
+            big = [(ms, by) for kind, ms, fl, by in recs_all if kind == k and by >= 2.56e8 and ms > 0]
+            if big:
+                gb = sum(b for _, b in big) / (sum(m for m, _ in big) * 1e-3) / 1e9
+                hbm[k]["launches_over_256MB"] = dict(count_per_step=len(big) / prof_steps, gb_per_s=gb,
+                                                     frac_of_hbm_peak=gb / pk["hbm_gbs"])
     cfg = dict(workload=workload, baseline_config=f"BASELINE.json configs[{w['config']}]", tile=TILE,
                timing="inputs (activations of a step >> 126 MB L2) larger than L2; no explicit flush; device-resident "
                       f"and end-to-end steps timed in {rounds} alternating segment pair(s)",
