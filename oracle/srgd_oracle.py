@@ -533,3 +533,194 @@ def tiled_sample(sd, spec, batch_size, condition_x, class_label=None, cond_scale
     top, bottom, left, right = ts["crop"]
     img = img[:, :, top:bottom, left:right].clamp(-1., 1.)
     return (img + 1) * 0.5
+
+
+# --------------------------------------------------------------------------------------------
+# EDM sampler family on the same U-Net: ConditionalElucidatedDiffusionSR,
+# model.py:2059-2560.  The preconditioning coefficients and the sigma schedule come from the pip
+# package's `ElucidatedDiffusion` base class, which is not under /root/reference: PARITY UNPINNED
+# for `edm_schedule` and `edm_coeffs` (restated from denoising-diffusion-pytorch 1.8.15 / Karras et
+# al. 2022, Table 1; the goldens were produced with the same restatement in oracle/_shim).
+# Everything else below follows the reference lines cited.  State-dict prefix of this family: "net.".
+# --------------------------------------------------------------------------------------------
+
+@dataclass(frozen=True)
+class EdmParams:
+    sigma_min: float = 0.002
+    sigma_max: float = 80
+    sigma_data: float = 0.5
+    rho: float = 7
+    S_churn: float = 80
+    S_tmin: float = 0.05
+    S_tmax: float = 50
+    S_noise: float = 1.003
+
+
+def edm_schedule(p: EdmParams, n: int, device=None) -> torch.Tensor:
+    """ElucidatedDiffusion.sample_schedule (pip, unpinned): n sigmas on the rho-grid + a trailing 0."""
+    inv_rho = 1 / p.rho
+    steps = torch.arange(n, device=device, dtype=torch.float32)
+    sigmas = (p.sigma_max ** inv_rho + steps / (n - 1) * (p.sigma_min ** inv_rho - p.sigma_max ** inv_rho)) ** p.rho
+    return F.pad(sigmas, (0, 1), value=0.)
+
+
+def edm_coeffs(p: EdmParams, sigma: torch.Tensor):
+    """c_in, c_out, c_skip, c_noise of the pip base class (unpinned), fp32 tensor arithmetic."""
+    sd2 = p.sigma_data ** 2
+    c_in = 1 * (sigma ** 2 + sd2) ** -0.5
+    c_out = sigma * p.sigma_data * (sd2 + sigma ** 2) ** -0.5
+    c_skip = sd2 / (sigma ** 2 + sd2)
+    c_noise = torch.log(sigma.clamp(min=1e-20)) * 0.25
+    return c_in, c_out, c_skip, c_noise
+
+
+def edm_denoise(sd, spec, p: EdmParams, x, sigma, condition_x, class_label, cond_scale=1.0, class_cond_scale=1.0,
+                clamp=False, prefix="net."):
+    """preconditioned_network_forward, model.py:2128-2183 (sigma: python float or [B] tensor)."""
+    b = x.shape[0]
+    if isinstance(sigma, float):
+        sigma = torch.full((b,), sigma, device=x.device)
+    pad = sigma.reshape(b, 1, 1, 1)
+    c_in, c_out, c_skip, _ = edm_coeffs(p, pad)
+    c_noise = edm_coeffs(p, sigma)[3]
+    out = c_skip * x + c_out * unet_forward(sd, spec, c_in * x, c_noise, class_label, condition_x, prefix=prefix)
+    if (cond_scale != 1.0) and (class_cond_scale != 1.0):
+        raise NotImplementedError(
+            "Currently, you cannot specify both cond_scale and class_cond_scale at the same time.")
+    if cond_scale != 1.0:
+        null = c_skip * x + c_out * unet_forward(sd, spec, c_in * x, c_noise, class_label, None, prefix=prefix)
+        out = null + (out - null) * cond_scale
+    if class_cond_scale != 1.0:
+        null = c_skip * x + c_out * unet_forward(sd, spec, c_in * x, c_noise, None, condition_x, prefix=prefix)
+        out = null + (out - null) * class_cond_scale
+    return out.clamp(-1., 1.) if clamp else out
+
+
+def _edm_gammas(p: EdmParams, sigmas, n):
+    """model.py:2234-2238."""
+    return torch.where((sigmas >= p.S_tmin) & (sigmas <= p.S_tmax), min(p.S_churn / n, math.sqrt(2) - 1), 0.)
+
+
+def _edm_heun(sd, spec, p, x_hat, sigma_hat, sigma_next, cond, label, cs, ccs, clamp):
+    """One Heun step on (a batch of tiles of) images_hat, model.py:2276-2289 / 2400-2410.
+    Returns (images_next, the x0-side quantity the reference records for with_x0_images / x_start)."""
+    out = edm_denoise(sd, spec, p, x_hat, sigma_hat, cond, label, cs, ccs, clamp)
+    d = (x_hat - out) / sigma_hat
+    nxt = x_hat + (sigma_next - sigma_hat) * d
+    if sigma_next != 0:
+        out2 = edm_denoise(sd, spec, p, nxt, sigma_next, cond, label, cs, ccs, clamp)
+        d2 = (nxt - out2) / sigma_next
+        nxt = x_hat + 0.5 * (sigma_next - sigma_hat) * (d + d2)
+        return nxt, d2
+    return nxt, d
+
+
+def edm_sample_heun(sd, spec, p: EdmParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
+                    guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                    generation_start_steps=0, num_sample_steps=32, clamp=True, zero_init=False, generator=None):
+    """sample_org, model.py:2213-2307 (condition_x in [0,1]; RNG call order preserved)."""
+    _n, _c, h, w = condition_x.shape
+    shape = (batch_size, spec.channels, h, w)
+    dev = condition_x.device
+    condition_x = condition_x * 2 - 1
+    sigmas = edm_schedule(p, num_sample_steps, dev)
+    gammas = _edm_gammas(p, sigmas, num_sample_steps)
+    if generation_start_steps > 0:                                        # get_noised_images, model.py:2186-2195
+        images = condition_x + sigmas[generation_start_steps] * torch.randn(condition_x.shape, generator=generator, device=dev)
+    elif zero_init:
+        images = torch.zeros(shape, device=dev)
+    else:
+        images = sigmas[0] * torch.randn(shape, generator=generator, device=dev)
+    for i in range(num_sample_steps):
+        if i < generation_start_steps:
+            continue
+        cs = 1.0 if i < guidance_start_steps else cond_scale
+        ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
+        sigma, sigma_next, gamma = sigmas[i].item(), sigmas[i + 1].item(), gammas[i].item()
+        eps = p.S_noise * torch.randn(shape, generator=generator, device=dev)
+        sigma_hat = sigma + gamma * sigma
+        images_hat = images + math.sqrt(sigma_hat ** 2 - sigma ** 2) * eps
+        images, _ = _edm_heun(sd, spec, p, images_hat, sigma_hat, sigma_next, condition_x, class_label, cs, ccs, clamp)
+    return (images.clamp(-1., 1.) + 1) * 0.5
+
+
+def edm_sample_dpmpp(sd, spec, p: EdmParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
+                     guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                     generation_start_steps=0, num_sample_steps=32, clamp=True, zero_init=False, generator=None):
+    """sample_using_dpmpp (DPM-Solver++ 2M), model.py:2466-2544."""
+    _n, _c, h, w = condition_x.shape
+    shape = (batch_size, spec.channels, h, w)
+    dev = condition_x.device
+    condition_x = condition_x * 2 - 1
+    sigmas = edm_schedule(p, num_sample_steps, dev)
+    if generation_start_steps > 0:
+        images = condition_x + sigmas[generation_start_steps] * torch.randn(condition_x.shape, generator=generator, device=dev)
+    elif zero_init:
+        images = torch.zeros(shape, device=dev)
+    else:
+        images = sigmas[0] * torch.randn(shape, generator=generator, device=dev)
+    t_fn = lambda s: s.log().neg()
+    sigma_fn = lambda t: t.neg().exp()
+    old = None
+    for i in range(len(sigmas) - 1):
+        if i < generation_start_steps:
+            continue
+        cs = 1.0 if i < guidance_start_steps else cond_scale
+        ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
+        den = edm_denoise(sd, spec, p, images, sigmas[i].item(), condition_x, class_label, cs, ccs, clamp)
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        hh = t_next - t
+        if old is None or sigmas[i + 1] == 0:
+            den_d = den
+        else:
+            r = (t - t_fn(sigmas[i - 1])) / hh
+            g = -1 / (2 * r)
+            den_d = (1 - g) * den + g * old
+        images = (sigma_fn(t_next) / sigma_fn(t)) * images - (-hh).expm1() * den_d
+        old = den
+    return (images.clamp(-1., 1.) + 1) * 0.5
+
+
+def edm_tiled_sample(sd, spec, p: EdmParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
+                     guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
+                     generation_start_steps=0, num_sample_steps=32, tile_size=256, tile_stride=256, clamp=True,
+                     zero_init=False, generator=None):
+    """tiled_sample of the EDM class (Heun), model.py:2309-2462: the whole canvas is perturbed first, the tiles of the
+    step's grid are denoised from images_hat in minibatches, and after odd steps everything outside the hull of the
+    shifted grid is replaced by sigma_i * noise (get_noised_images(zeros, i): the CURRENT step's sigma)."""
+    dev = condition_x.device
+    ts = tiled_setup(condition_x, tile_size, tile_stride)
+    padded, masked = ts["padded"], ts["masked"]
+    shape = padded.shape
+    sigmas = edm_schedule(p, num_sample_steps, dev)
+    gammas = _edm_gammas(p, sigmas, num_sample_steps)
+    if generation_start_steps > 0:
+        images = padded + sigmas[generation_start_steps] * torch.randn(shape, generator=generator, device=dev)
+    elif zero_init:
+        images = torch.zeros(shape, device=dev)
+    else:
+        images = sigmas[0] * torch.randn(shape, generator=generator, device=dev)
+    stop, sbottom, sleft, sright = ts["hull"]
+    for i in range(num_sample_steps):
+        if i < generation_start_steps:
+            continue
+        cs = 1.0 if i < guidance_start_steps else cond_scale
+        ccs = 1.0 if i < class_guidance_start_steps else class_cond_scale
+        sigma, sigma_next, gamma = sigmas[i].item(), sigmas[i + 1].item(), gammas[i].item()
+        eps = p.S_noise * torch.randn(shape, generator=generator, device=dev)
+        sigma_hat = sigma + gamma * sigma
+        images_hat = images + math.sqrt(sigma_hat ** 2 - sigma ** 2) * eps
+        cur = ts["coord_list"][i % 2]
+        for s0 in range(0, len(cur), batch_size):
+            chunk = cur[s0:s0 + batch_size]
+            mb = torch.cat([images_hat[:, :, hs:he, ws:we] for hs, he, ws, we in chunk], 0)
+            mc = torch.cat([masked[:, :, hs:he, ws:we] for hs, he, ws, we in chunk], 0)
+            nxt, _ = _edm_heun(sd, spec, p, mb, sigma_hat, sigma_next, mc, class_label, cs, ccs, clamp)
+            for k, (hs, he, ws, we) in enumerate(chunk):
+                images[:, :, hs:he, ws:we] = nxt[k]
+        if i % 2 == 1:
+            cropped = images[:, :, stop:sbottom, sleft:sright]
+            images = sigmas[i] * torch.randn(shape, generator=generator, device=dev)     # zeros + sigma_i * noise
+            images[:, :, stop:sbottom, sleft:sright] = cropped
+    top, bottom, left, right = ts["crop"]
+    return (images[:, :, top:bottom, left:right].clamp(-1., 1.) + 1) * 0.5
