@@ -67,6 +67,37 @@ int srgd_sampler_step(const float* x, const float* eps_cond, const float* eps_nu
                       const float* noise, float* img_next, float* x_start, int64_t n,
                       const srgd_step_scalars* s, srgd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * EDM sampler family on the same U-Net (ConditionalElucidatedDiffusionSR, model.py:2059-2560; SURVEY.md section 8
+ * f-4).  Scalars are computed by the host like the reference does (python doubles / fp32 tensor math) and passed
+ * as fp32.  All buffers fp32, n elements; optional pointers may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+/* images_hat = images + coef * (s_noise * noise)  (model.py:2270-2273; noise NULL: images_hat = images) and
+ * x_in = c_in * images_hat, the scaled input of the next U-Net evaluation (model.py:2141). */
+int srgd_edm_perturb(const float* images, const float* noise, float s_noise, float coef, float c_in,
+                     float* images_hat, float* x_in, int64_t n, srgd_stream_t stream);
+
+typedef struct srgd_edm_scalars {
+  float c_skip, c_out;      /* preconditioning at sigma_eval                              model.py:2147      */
+  float guidance_scale;     /* s in  out = null + (out - null) * s                        model.py:2165, 2178 */
+  float sigma_eval;         /* d = (x_eval - denoised) / sigma_eval                       model.py:2279, 2287 */
+  float step;               /* images = x_base + step * (d_prev + d): sigma_next - sigma_hat for the Euler stage,
+                               0.5 * (sigma_next - sigma_hat) for the Heun correction     model.py:2281, 2289 */
+  float c_in_next;          /* x_in_out = c_in_next * images                                                  */
+  int32_t clip;             /* clamp the denoised image to [-1, 1]                        model.py:2180      */
+} srgd_edm_scalars;
+/* preconditioned_network_forward's combine (c_skip x + c_out net, classifier-free guidance against net_null, clamp;
+ * model.py:2148-2183) fused with the sampler update that consumes it.  Outputs (each optional): images_out (needs
+ * x_base; d_prev optional), d_out = (x_eval - denoised) / sigma_eval, denoised_out, x_in_out = c_in_next * images_out. */
+int srgd_edm_update(const float* x_eval, const float* net_cond, const float* net_null, const float* x_base,
+                    const float* d_prev, float* images_out, float* d_out, float* denoised_out, float* x_in_out,
+                    int64_t n, const srgd_edm_scalars* s, srgd_stream_t stream);
+/* DPM-Solver++ (2M) update (model.py:2521-2530): denoised_d = w_new * denoised + w_old * old_denoised (old NULL:
+ * denoised_d = denoised); images_out = a * images - b * denoised_d; x_in_out = c_in_next * images_out. */
+int srgd_edm_dpmpp(const float* images, const float* denoised, const float* old_denoised, float a, float b,
+                   float w_new, float w_old, float c_in_next, float* images_out, float* x_in_out, int64_t n,
+                   srgd_stream_t stream);
+
 /* q_sample (model.py:3434-3447): out = x_start*alpha + noise*sigma.  x_start may be NULL (zeros). */
 int srgd_q_sample(const float* x_start, const float* noise, float* out, int64_t n, float alpha,
                   float sigma, srgd_stream_t stream);

@@ -14,8 +14,10 @@ import torch.nn as nn
 
 from srgd_b200 import (ConditionalContinuousTimeGaussianDiffusionSR, ConditionalSRUnet, alpha_cosine_log_snr,
                        beta_linear_log_snr, get_area, get_coord_and_pad, get_coords)
+from srgd_b200.edm import ConditionalElucidatedDiffusionSR
 
-__all__ = ["ConditionalSRUnet", "ConditionalContinuousTimeGaussianDiffusionSR", "get_model", "ModelEma",
+__all__ = ["ConditionalSRUnet", "ConditionalContinuousTimeGaussianDiffusionSR", "ConditionalElucidatedDiffusionSR",
+           "get_model", "ModelEma",
            "beta_linear_log_snr", "alpha_cosine_log_snr", "get_coord_and_pad", "get_coords", "get_area",
            "normalize_to_neg_one_to_one", "unnormalize_to_zero_to_one"]
 
@@ -42,10 +44,12 @@ class ModelEma(nn.Module):
 
 
 def get_model(conf, logger):
-    """reference model.py:3500-3666, conditional_continuous branch."""
-    if conf.model != 'conditional_continuous':
+    """reference model.py:3500-3666: the shipped conditional_continuous branch (3503-3515, 3634-3651) and the
+    conditional_elucidated branch (EDM sampler family on the same U-Net, 3593-3614)."""
+    if conf.model not in ('conditional_continuous', 'conditional_elucidated'):
         raise NotImplementedError(
-            f"conf.model={conf.model!r}: srgd_b200 builds the shipped 'conditional_continuous' sampler only")
+            f"conf.model={conf.model!r}: srgd_b200 builds the class-conditional samplers 'conditional_continuous' "
+            "(shipped) and 'conditional_elucidated' only")
     assert conf.learned_sinusoidal_cond
     dim_mults = tuple(int(v) for v in str(conf.ddpm_unet_dim_mults).split(','))
     full_attn = tuple(v.strip() == 'True' for v in str(conf.full_attn).split(','))
@@ -66,6 +70,16 @@ def get_model(conf, logger):
     assert unet.spec == spec
     logger.info(f"ConditionalSRUnet: channels=6 dim={conf.unet_dim} dim_mults={conf.ddpm_unet_dim_mults} "
                 f"num_classes={conf.num_classes}")
+    if conf.model == 'conditional_elucidated':
+        diffusion = ConditionalElucidatedDiffusionSR(
+            unet, image_size=conf.image_size, num_sample_steps=conf.num_sample_steps, sigma_min=conf.sigma_min,
+            sigma_max=conf.sigma_max, sigma_data=conf.sigma_data, rho=conf.rho, P_mean=conf.P_mean, P_std=conf.P_std,
+            S_churn=conf.S_churn, S_tmin=conf.S_tmin, S_tmax=conf.S_tmax, S_noise=conf.S_noise,
+            cond_drop_prob=conf.cond_drop_prob, class_cond_drop_prob=conf.class_cond_drop_prob,
+            use_dpmpp_solver=conf.use_dpmpp_solver, loss_type=conf.loss_type)
+        logger.info(f"ConditionalElucidatedDiffusionSR: image_size={conf.image_size} "
+                    f"num_sample_steps={conf.num_sample_steps}")
+        return _finish(conf, logger, diffusion, unet, spec, ckpt_path, use_cache, cached, _weights)
     conf.use_dpmpp_solver = False
     diffusion = ConditionalContinuousTimeGaussianDiffusionSR(
         model=unet, image_size=conf.image_size, noise_schedule=conf.noise_schedule,
@@ -77,9 +91,15 @@ def get_model(conf, logger):
         loss_type=conf.loss_type)
     logger.info(f"ConditionalContinuousTimeGaussianDiffusionSR: image_size={conf.image_size} "
                 f"num_sample_steps={conf.num_sample_steps}")
+    return _finish(conf, logger, diffusion, unet, spec, ckpt_path, use_cache, cached, _weights)
+
+
+def _finish(conf, logger, diffusion, unet, spec, ckpt_path, use_cache, cached, _weights):
+    """EMA holder + checkpoint (model.py:3657-3664), through the ingest cache when there is one."""
     ema_model = ModelEma(diffusion, decay=conf.ema_decay, copy_model=False)
     if ckpt_path and cached is not None:
-        ema_model.module.model.attach_pack_cache(cached, ckpt_path)
+        unet.attach_pack_cache(cached, ckpt_path,
+                               prefix="net." if isinstance(diffusion, ConditionalElucidatedDiffusionSR) else "model.")
         logger.info(f"load ema_model weight from : {ckpt_path} (ingest cache {_weights.pack_cache_path(ckpt_path)}; "
                     "fp32 parameters are read from the checkpoint on first state_dict())")
     elif ckpt_path:
@@ -88,5 +108,5 @@ def get_model(conf, logger):
         logger.info(f"load ema_model weight from : {ckpt_path}")
         logger.info(f"check: {check}")
         if use_cache and not check.missing_keys and not check.unexpected_keys:
-            ema_model.module.model.save_pack_cache_after_first_pack(ckpt_path)
+            unet.save_pack_cache_after_first_pack(ckpt_path)
     return ema_model

@@ -617,8 +617,10 @@ def _edm_heun(sd, spec, p, x_hat, sigma_hat, sigma_next, cond, label, cs, ccs, c
 
 def edm_sample_heun(sd, spec, p: EdmParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
                     guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
-                    generation_start_steps=0, num_sample_steps=32, clamp=True, zero_init=False, generator=None):
-    """sample_org, model.py:2213-2307 (condition_x in [0,1]; RNG call order preserved)."""
+                    generation_start_steps=0, num_sample_steps=32, clamp=True, zero_init=False, generator=None,
+                    model_steps=None):
+    """sample_org, model.py:2213-2307 (condition_x in [0,1]; RNG call order preserved).  `model_steps` = the object's
+    own num_sample_steps, whose schedule get_noised_images uses (model.py:2189, 2241); default: num_sample_steps."""
     _n, _c, h, w = condition_x.shape
     shape = (batch_size, spec.channels, h, w)
     dev = condition_x.device
@@ -626,7 +628,8 @@ def edm_sample_heun(sd, spec, p: EdmParams, batch_size, condition_x, class_label
     sigmas = edm_schedule(p, num_sample_steps, dev)
     gammas = _edm_gammas(p, sigmas, num_sample_steps)
     if generation_start_steps > 0:                                        # get_noised_images, model.py:2186-2195
-        images = condition_x + sigmas[generation_start_steps] * torch.randn(condition_x.shape, generator=generator, device=dev)
+        images = condition_x + edm_schedule(p, model_steps or num_sample_steps, dev)[generation_start_steps] * \
+            torch.randn(condition_x.shape, generator=generator, device=dev)
     elif zero_init:
         images = torch.zeros(shape, device=dev)
     else:
@@ -684,7 +687,7 @@ def edm_sample_dpmpp(sd, spec, p: EdmParams, batch_size, condition_x, class_labe
 def edm_tiled_sample(sd, spec, p: EdmParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
                      guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0,
                      generation_start_steps=0, num_sample_steps=32, tile_size=256, tile_stride=256, clamp=True,
-                     zero_init=False, generator=None):
+                     zero_init=False, generator=None, model_steps=None):
     """tiled_sample of the EDM class (Heun), model.py:2309-2462: the whole canvas is perturbed first, the tiles of the
     step's grid are denoised from images_hat in minibatches, and after odd steps everything outside the hull of the
     shifted grid is replaced by sigma_i * noise (get_noised_images(zeros, i): the CURRENT step's sigma)."""
@@ -720,7 +723,8 @@ def edm_tiled_sample(sd, spec, p: EdmParams, batch_size, condition_x, class_labe
                 images[:, :, hs:he, ws:we] = nxt[k]
         if i % 2 == 1:
             cropped = images[:, :, stop:sbottom, sleft:sright]
-            images = sigmas[i] * torch.randn(shape, generator=generator, device=dev)     # zeros + sigma_i * noise
+            images = edm_schedule(p, model_steps or num_sample_steps, dev)[i] * \
+                torch.randn(shape, generator=generator, device=dev)                       # zeros + sigma_i * noise
             images[:, :, stop:sbottom, sleft:sright] = cropped
     top, bottom, left, right = ts["crop"]
     return (images[:, :, top:bottom, left:right].clamp(-1., 1.) + 1) * 0.5

@@ -28,6 +28,11 @@ class StepScalars(C.Structure):
                 ("noise_scale", C.c_float), ("guidance_scale", C.c_float), ("clip", C.c_int32)]
 
 
+class EdmScalars(C.Structure):
+    _fields_ = [("c_skip", C.c_float), ("c_out", C.c_float), ("guidance_scale", C.c_float), ("sigma_eval", C.c_float),
+                ("step", C.c_float), ("c_in_next", C.c_float), ("clip", C.c_int32)]
+
+
 SRGD_MAX_TILES_PER_CALL = 64
 
 
@@ -71,6 +76,9 @@ SIGNATURES = {
     "srgd_last_error": (C.c_char_p, []),
     "srgd_device_check": (C.c_int, [C.c_int]),
     "srgd_sampler_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(StepScalars), _P]),
+    "srgd_edm_perturb": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _I64, _P]),
+    "srgd_edm_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(EdmScalars), _P]),
+    "srgd_edm_dpmpp": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _I64, _P]),
     "srgd_q_sample": (C.c_int, [_P, _P, _P, _I64, C.c_float, C.c_float, _P]),
     "srgd_finalize_image": (C.c_int, [_P, _P, _I64, _P]),
     "srgd_gather_tiles": (C.c_int, [_P, _P, C.POINTER(TileCoords), _I32, _I32, _I32, _I32, _P]),

@@ -141,10 +141,12 @@ class ConditionalSRUnet(nn.Module):
         module._deferred_ckpt = None
         module._drop_handle()
 
-    def attach_pack_cache(self, pack: Dict[str, torch.Tensor], ckpt_path: str) -> None:
-        """Start from the ingest cache of `ckpt_path` (weights.load_pack_cache) instead of its fp32 state dict."""
+    def attach_pack_cache(self, pack: Dict[str, torch.Tensor], ckpt_path: str, prefix: str = "model.") -> None:
+        """Start from the ingest cache of `ckpt_path` (weights.load_pack_cache) instead of its fp32 state dict;
+        `prefix` = the U-Net's key prefix inside ckpt['ema_model'] ("model." / "net." by sampler family)."""
         self._drop_handle()
         self._cached_pack, self._deferred_ckpt = pack, ckpt_path
+        self.__dict__["_ckpt_prefix"] = prefix
 
     def save_pack_cache_after_first_pack(self, ckpt_path: str) -> None:
         self._save_pack_for = ckpt_path
@@ -155,7 +157,8 @@ class ConditionalSRUnet(nn.Module):
             return
         path, self._deferred_ckpt = self._deferred_ckpt, None
         sd = torch.load(path, map_location="cpu", weights_only=True)["ema_model"]
-        own = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+        prefix = self.__dict__.get("_ckpt_prefix", "model.")
+        own = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
         pack, handle_state = self._cached_pack, (self._handle, self._packed, self._packed_key)
         with torch.no_grad():
             for k, p in super().state_dict(keep_vars=True).items():

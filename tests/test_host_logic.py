@@ -281,3 +281,27 @@ def test_ingest_cache_validation_and_deferred_fp32(tmp_path):
     # loading other weights detaches the cache
     ema.module.load_state_dict(sd, strict=True)
     assert unet._cached_pack is None
+
+
+def test_get_model_builds_the_edm_family(tmp_path):
+    """conf.model == 'conditional_elucidated' (model.py:3593-3614): same U-Net under the key prefix `net.`, the
+    reference's constructor arguments, checkpoint round trip."""
+    import logging
+    import config as Cfg
+    import model as M
+    yaml_path = tmp_path / "c.yaml"
+    yaml_path.write_text("model: conditional_elucidated\nunet_dim: 64\nimage_size: 64\nnum_sample_steps: 32\n"
+                         "learned_sinusoidal_cond: true\nlearned_sinusoidal_dim: 32\nsigma_max: 60\n")
+    conf = Cfg.load_config(str(yaml_path))
+    sd = O.make_state_dict(O.UnetSpec(dim=64), 5, prefix="net.")
+    ck = tmp_path / "w.pth"
+    torch.save({"ema_model": sd}, ck)
+    conf.ckpt_path = str(ck)
+    edm = M.get_model(conf, logging.getLogger("t")).module
+    assert isinstance(edm, M.ConditionalElucidatedDiffusionSR) and edm.sigma_max == 60 and edm.use_dpmpp_solver is True
+    got = edm.state_dict()
+    assert list(got) == list(sd) and all(torch.equal(got[k], v) for k, v in sd.items())
+    s = edm.sample_schedule(8)
+    assert s.shape == (9,) and abs(float(s[0]) - 60.0) < 1e-4 and float(s[-1]) == 0.0 and abs(float(s[-2]) - 0.002) < 1e-6
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        edm.sample(batch_size=1, condition_x=torch.rand(1, 3, 64, 64), num_sample_steps=4)

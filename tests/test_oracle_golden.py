@@ -176,3 +176,29 @@ def test_step_gating_options(golden_dir):
     t = O.tiled_sample(sd, spec, 4, cond_t, torch.tensor([2]), class_cond_scale=2.0, class_guidance_start_steps=2,
                        generation_start_steps=1, num_sample_steps=4)
     torch.testing.assert_close(t[..., ::2, ::2], T(g["tiled_a_sub2"]), rtol=0, atol=5e-4)
+
+
+def test_edm_family_oracle_vs_reference_golden(golden_dir):
+    """the oracle's restatement of ConditionalElucidatedDiffusionSR (model.py:2059-2560) against
+    outputs of the unmodified reference class (tests/golden/make_golden_edm.py): preconditioned forward with each
+    guidance kind, stochastic Heun sample_org (incl. generation_start_steps + guidance_start_steps), DPM-Solver++ 2M,
+    Heun tiled_sample -- bit-exact.  (The pip base class behind both is the shim's restatement: parity unpinned.)"""
+    g = _load(golden_dir, "edm_tiny")
+    T = lambda a: torch.from_numpy(np.asarray(a))
+    spec, p = O.UnetSpec(dim=16), O.EdmParams()
+    sd = O.make_state_dict(spec, 11, prefix="net.")
+    cond, big, x, label, n = T(g["cond"]), T(g["big"]), T(g["x"]), T(g["label"]), int(g["steps"])
+    gen = lambda: torch.Generator().manual_seed(71)
+    with torch.inference_mode():
+        for name in ("fwd_plain", "fwd_class", "fwd_cond"):
+            sig, cs, ccs = (float(v) for v in g[name + "_meta"])
+            assert torch.equal(O.edm_denoise(sd, spec, p, x, sig, cond * 2 - 1, label, cs, ccs, clamp=True), T(g[name])), name
+        assert torch.equal(O.edm_sample_heun(sd, spec, p, 2, cond, label, class_cond_scale=2.0, num_sample_steps=n,
+                                             generator=gen()), T(g["heun_class"]))
+        assert torch.equal(O.edm_sample_heun(sd, spec, p, 1, cond[:1], label, cond_scale=1.5, guidance_start_steps=3,
+                                             generation_start_steps=2, num_sample_steps=n, generator=gen()),
+                           T(g["heun_cond_start2"]))
+        assert torch.equal(O.edm_tiled_sample(sd, spec, p, 5, big, label, class_cond_scale=2.0, num_sample_steps=n,
+                                              tile_size=32, tile_stride=32, generator=gen()), T(g["tiled_heun"]))
+        assert torch.equal(O.edm_sample_dpmpp(sd, spec, p, 2, cond, label, class_cond_scale=2.0, num_sample_steps=n,
+                                              generator=gen()), T(g["dpmpp_class"]))
