@@ -1,10 +1,11 @@
 """Drop-in `model` module: the names `inference.py` and user code import from the reference's
 model.py, backed by the srgd_b200 CUDA library.
 
-Only the path the shipped configuration selects is built (conf.model == 'conditional_continuous',
-reference model.py:3503-3515 + 3634-3651): `ConditionalSRUnet` and
-`ConditionalContinuousTimeGaussianDiffusionSR`.  Other `conf.model` values raise
-NotImplementedError (no configuration or weights ship for them).
+Built: the path the shipped configuration selects (conf.model == 'conditional_continuous', reference
+model.py:3503-3515 + 3634-3651: `ConditionalSRUnet` + `ConditionalContinuousTimeGaussianDiffusionSR`) and the
+class-conditional EDM sampler family on the same U-Net (conf.model == 'conditional_elucidated', model.py:3593-3614:
+`ConditionalElucidatedDiffusionSR`).  Other `conf.model` values raise NotImplementedError (the non-conditional
+twins and the discrete DDPM / DDIM family; no configuration or weights ship for them).
 """
 import copy
 import os
@@ -12,9 +13,8 @@ import os
 import torch
 import torch.nn as nn
 
-from srgd_b200 import (ConditionalContinuousTimeGaussianDiffusionSR, ConditionalSRUnet, alpha_cosine_log_snr,
-                       beta_linear_log_snr, get_area, get_coord_and_pad, get_coords)
-from srgd_b200.edm import ConditionalElucidatedDiffusionSR
+from srgd_b200 import (ConditionalContinuousTimeGaussianDiffusionSR, ConditionalElucidatedDiffusionSR, ConditionalSRUnet,
+                       alpha_cosine_log_snr, beta_linear_log_snr, get_area, get_coord_and_pad, get_coords)
 
 __all__ = ["ConditionalSRUnet", "ConditionalContinuousTimeGaussianDiffusionSR", "ConditionalElucidatedDiffusionSR",
            "get_model", "ModelEma",
