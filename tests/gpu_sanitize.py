@@ -1,6 +1,6 @@
 """compute-sanitizer driver (not a pytest test): two p_sample steps of a dim-64 U-Net on a 128x64 tile batch of 2 with
 classifier-free guidance -- every kernel family of the hot path (both conv kernels incl. the halo variant is skipped at
-this width, fused linear attention, tcgen05 flash attention, GroupNorm apply with folded statistics, sampler update).
+this width, fused linear attention, tcgen05 flash attention, GroupNorm apply with folded statistics, sampler update; round 2: split-K conv tiles, class-guidance sharing, staged LinearAttention stores, the EDM kernels).
 
     compute-sanitizer --tool memcheck  python tests/gpu_sanitize.py
     compute-sanitizer --tool racecheck python tests/gpu_sanitize.py
@@ -32,7 +32,13 @@ def main():
     with torch.inference_mode():
         for i in (100, 101):
             x, _ = diff.p_sample(x, steps[i], cond, torch.tensor([1], device="cuda"), 1.0, 3.0, steps[i + 1])
+        # the EDM family's fused kernels (perturb / update incl. the Heun correction) around the same U-Net
+        edm = M.ConditionalElucidatedDiffusionSR(unet, image_size=H, num_sample_steps=4).eval().to("cuda:0")
+        edm.progress = False
+        y = edm.sample(batch_size=2, condition_x=(cond + 1) * 0.5, class_label=torch.tensor([1], device="cuda"),
+                       class_cond_scale=2.0, num_sample_steps=2)
     torch.cuda.synchronize()
+    print("edm:", float(y.mean()))
     print("sanitize run finished:", float(x.abs().mean()), diff.last_step_launches, "launches per step")
 
 
