@@ -339,7 +339,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           const int want = 8 * (p.split - 1);
           const long long t0 = clock64();
           while (ld_acquire_gpu(p.sk_flags + wi.slot) < want) {
-            if (clock64() - t0 > 4000000000LL) {
+            // ~60 s: the partner is another CTA that may be slowed down 100x by compute-sanitizer's instrumentation
+            if (clock64() - t0 > 120000000000LL) {
               printf("srgd_b200: split-K wait timed out (block %d slot %d)\n", (int)blockIdx.x, wi.slot);
               __trap();
             }
