@@ -553,49 +553,59 @@ __global__ void __launch_bounds__(320, 1) la_out_kernel(const __grid_constant__ 
       named_bar_sync(1, 256);
       const float tot = ssq_t[row] + ssq_t[128 + row];
       const float scale = sqrt_c / fmaxf(sqrtf(tot), 1e-12f);
-      const bf16* xrow = p.x + px * C + c_first;
-      // Output rows go through this warp's own 4 KB of the softmax(q) operand tile (free once the Y MMA has completed):
-      // 64 columns are written row-wise, then read back so that eight lanes cover one row's 128 bytes -- a store
-      // instruction touches 4 full lines instead of 32 half sectors.
+      // Residual rows in and output rows out go through this warp's own 4 KB of the softmax(q) operand tile (free once
+      // the Y MMA has completed), 64 columns at a time: global accesses are made with eight lanes per row (128 bytes),
+      // so an instruction touches 4 full lines instead of 32 half sectors, and the tile transposes between that
+      // layout and one row per thread.
       const int64_t px0 = (int64_t)(b * p.tiles_per_sample + t0 + it) * 128 + q * 32;
+      const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll 1
-      for (int cc = 0; cc < kYChunks; ++cc) {
-        uint4 xr[4];
+      for (int cp = 0; cp < kYChunks / 2; ++cp) {
+        uint4 xr[8];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) xr[jj] = *reinterpret_cast<const uint4*>(xrow + cc * 32 + jj * 8);
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + lane_bits + ycol0 + cc * 32, v);
-        ptx::tmem_ld_wait();
+        for (int k = 0; k < 8; ++k)
+          xr[k] = *reinterpret_cast<const uint4*>(p.x + (px0 + k * 4 + sub) * C + c_first + cp * 64 + chunk * 8);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float r[8], o[8];
-          unpack8(xr[jj], r);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8 + 4));
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8 + 4));
-          o[0] = (__uint_as_float(v[jj * 8 + 0]) + b0.x) * scale * g0.x + r[0];
-          o[1] = (__uint_as_float(v[jj * 8 + 1]) + b0.y) * scale * g0.y + r[1];
-          o[2] = (__uint_as_float(v[jj * 8 + 2]) + b0.z) * scale * g0.z + r[2];
-          o[3] = (__uint_as_float(v[jj * 8 + 3]) + b0.w) * scale * g0.w + r[3];
-          o[4] = (__uint_as_float(v[jj * 8 + 4]) + b1.x) * scale * g1.x + r[4];
-          o[5] = (__uint_as_float(v[jj * 8 + 5]) + b1.y) * scale * g1.y + r[5];
-          o[6] = (__uint_as_float(v[jj * 8 + 6]) + b1.z) * scale * g1.z + r[6];
-          o[7] = (__uint_as_float(v[jj * 8 + 7]) + b1.w) * scale * g1.w + r[7];
-          const uint4 pk = pack8(o);
-          st_shared_v4(qs_smem + ptx::sw128_offset(row, (cc & 1) * 4 + jj), pk.x, pk.y, pk.z, pk.w);
-        }
-        if (cc & 1) {
-          __syncwarp();
-          const int sub = lane >> 3, chunk = lane & 7;
+        for (int k = 0; k < 8; ++k)
+          st_shared_v4(qs_smem + ptx::sw128_offset(q * 32 + k * 4 + sub, chunk), xr[k].x, xr[k].y, xr[k].z, xr[k].w);
+        __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rl = k * 4 + sub;
-            const uint4 pk = ld_shared_v4(qs_smem + ptx::sw128_offset(q * 32 + rl, chunk));
-            st_stream(p.out + (px0 + rl) * C + c_first + (cc >> 1) * 64 + chunk * 8, pk);
+        for (int t = 0; t < 8; ++t) xr[t] = ld_shared_v4(qs_smem + ptx::sw128_offset(row, t));
+        __syncwarp();
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cc = cp * 2 + c2;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_bits + ycol0 + cc * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float r[8], o[8];
+            unpack8(xr[c2 * 4 + jj], r);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_first + cc * 32 + jj * 8 + 4));
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.g + c_first + cc * 32 + jj * 8 + 4));
+            o[0] = (__uint_as_float(v[jj * 8 + 0]) + b0.x) * scale * g0.x + r[0];
+            o[1] = (__uint_as_float(v[jj * 8 + 1]) + b0.y) * scale * g0.y + r[1];
+            o[2] = (__uint_as_float(v[jj * 8 + 2]) + b0.z) * scale * g0.z + r[2];
+            o[3] = (__uint_as_float(v[jj * 8 + 3]) + b0.w) * scale * g0.w + r[3];
+            o[4] = (__uint_as_float(v[jj * 8 + 4]) + b1.x) * scale * g1.x + r[4];
+            o[5] = (__uint_as_float(v[jj * 8 + 5]) + b1.y) * scale * g1.y + r[5];
+            o[6] = (__uint_as_float(v[jj * 8 + 6]) + b1.z) * scale * g1.z + r[6];
+            o[7] = (__uint_as_float(v[jj * 8 + 7]) + b1.w) * scale * g1.w + r[7];
+            const uint4 pk = pack8(o);
+            st_shared_v4(qs_smem + ptx::sw128_offset(row, c2 * 4 + jj), pk.x, pk.y, pk.z, pk.w);
           }
-          __syncwarp();
         }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rl = k * 4 + sub;
+          const uint4 pk = ld_shared_v4(qs_smem + ptx::sw128_offset(q * 32 + rl, chunk));
+          st_stream(p.out + (px0 + rl) * C + c_first + cp * 64 + chunk * 8, pk);
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before();
     }

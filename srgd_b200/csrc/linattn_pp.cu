@@ -557,17 +557,34 @@ __global__ void __launch_bounds__(576, 1) la_out_pp_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&qs_ready[g]);
 
-      // residual row (L2-hot: the TMA fetched the same lines), requested while the Y MMA runs.  (Taking it from the x
-      // ring slot instead -- slot handed back by the epilogue -- was tried in round 2: nondeterministic results at
-      // B=16, 128x128, cause not found; profiles/r02_experiments.txt.)
-      const bf16* xrow = p.x + px * C + half * 64;
+      // residual rows (L2-hot: the TMA fetched the same lines), requested while the Y MMA runs.  Loaded COALESCED --
+      // eight lanes cover one row's 128 bytes, a load instruction touches 4 full lines instead of 32 half sectors (the
+      // L1 data pipe was 70 % busy) -- and transposed to one row per thread through the warp's staging rows below.
+      // (Taking them from the x ring slot instead, slot handed back by the epilogue, was tried in round 2:
+      // nondeterministic results at B=16, 128x128, cause not found; profiles/r02_experiments.txt.)
       uint4 xr[8];
+      {
+        const int64_t px0 = row0 + (int64_t)(2 * it + g) * 128 + q * 32;
+        const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) xr[t] = *reinterpret_cast<const uint4*>(xrow + t * 8);
+        for (int k = 0; k < 8; ++k)
+          xr[k] = *reinterpret_cast<const uint4*>(p.x + (px0 + k * 4 + sub) * C + half * 64 + chunk * 8);
+      }
 
       // ---- y: + bias, RMSNorm over all 128 channels of the pixel (model.py:207), * g, + x ----
       ptx::mbar_wait(&y_full[g], par);
       ptx::tc_fence_after();
+      {
+        // the Y MMA has consumed the softmax(q) operand: this warp's 4 KB of it are free -> transpose the residual
+        const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::sts_v4(qs_addr + ptx::sw128_offset(q * 32 + k * 4 + sub, chunk), xr[k].x, xr[k].y, xr[k].z, xr[k].w);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xr[t] = ptx::lds_v4(qs_addr + ptx::sw128_offset(row, t));
+        __syncwarp();                                      // the rows are rewritten by the output staging below
+      }
       float ssq = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
