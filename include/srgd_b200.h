@@ -98,6 +98,34 @@ int srgd_edm_dpmpp(const float* images, const float* denoised, const float* old_
                    float w_new, float w_old, float c_in_next, float* images_out, float* x_in_out, int64_t n,
                    srgd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Discrete-time sampler family on the same U-Net (ConditionalGaussianDiffusionSR, model.py:1311-1660: DDPM
+ * ancestral sampling and DDIM).  The per-timestep coefficients are entries of the
+ * reference's registered fp32 buffers (model.py:1395-1424), looked up by the host and passed as scalars.
+ * ------------------------------------------------------------------------------------------ */
+enum { SRGD_OBJ_PRED_NOISE = 0, SRGD_OBJ_PRED_X0 = 1, SRGD_OBJ_PRED_V = 2 };          /* model.py:1472-1489 */
+enum { SRGD_GAUSS_DDPM = 0,        /* p_sample: posterior mean + exp(0.5 log var) * noise    model.py:1503-1514 */
+       SRGD_GAUSS_DDIM = 1,        /* ddim_sample step with time_next >= 0                   model.py:1608-1622 */
+       SRGD_GAUSS_DDIM_LAST = 2 }; /* ddim_sample step with time_next < 0: img = x_start     model.py:1604-1605 */
+typedef struct srgd_gauss_scalars {
+  int32_t objective, mode;
+  int32_t clip;             /* clamp x_start to [-1, 1] (clip_x_start, or p_mean_variance's clamp_)  1471, 1497 */
+  int32_t rederive;         /* rederive_pred_noise (only read for objective pred_noise)              1477-1478 */
+  float guidance_scale;     /* s in  out = null + (cond - null) * s                                  1464, 1468 */
+  float sqrt_recip_ac, sqrt_recipm1_ac;   /* sqrt_recip_alphas_cumprod[t], sqrt_recipm1_alphas_cumprod[t]        */
+  float sqrt_ac, sqrt_1m_ac;              /* sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t] (pred_v)   */
+  float coef1, coef2;                     /* posterior_mean_coef1[t], posterior_mean_coef2[t]        (DDPM)      */
+  float noise_scale;                      /* DDPM: exp(0.5 * posterior_log_variance_clipped[t]); DDIM: sigma    */
+  float sqrt_ac_next, c;                  /* DDIM: sqrt(alphas_cumprod[t_next]), sqrt(1 - alpha_next - sigma^2) */
+} srgd_gauss_scalars;
+/* model_predictions (guidance combine, x_start, clamp, pred_noise; model.py:1449-1489) fused with the update that
+ * consumes it.  out_null / noise may be NULL (no guidance / no noise term); each of img_out, x_start_out,
+ * pred_noise_out is optional but at least one is required.  pred_noise_out is the noise AFTER the clamp when the
+ * objective or `rederive` derives it from x_start. */
+int srgd_gauss_update(const float* x_t, const float* out_cond, const float* out_null, const float* noise,
+                      float* img_out, float* x_start_out, float* pred_noise_out, int64_t n,
+                      const srgd_gauss_scalars* s, srgd_stream_t stream);
+
 /* q_sample (model.py:3434-3447): out = x_start*alpha + noise*sigma.  x_start may be NULL (zeros). */
 int srgd_q_sample(const float* x_start, const float* noise, float* out, int64_t n, float alpha,
                   float sigma, srgd_stream_t stream);
@@ -283,6 +311,10 @@ int srgd_dense_rows(const float* x, const float* w, const float* bias, float* y,
 /* [log_snr, sin(2 pi w log_snr), cos(...)]  (model.py:233-238): out fp32 [B][2*half+1]. */
 int srgd_fourier_features(const float* log_snr, const float* weights, float* out, int32_t B,
                           int32_t half_dim, srgd_stream_t stream);
+/* SinusoidalPosEmb (model.py:209-221): out fp32 [B][2*half], [sin(t * freq) | cos(t * freq)];  freq[k] =
+ * exp(-k * ln(10000) / (half - 1)) is tabulated by the packer with the reference's own torch ops. */
+int srgd_sinusoidal_pos_emb(const float* t, const float* freq, float* out, int32_t B, int32_t half_dim,
+                            srgd_stream_t stream);
 /* t[b][:] += table[labels[b]][:] for labels[b] >= 0   (t = t + class_mlp(label), model.py:692-694) */
 int srgd_add_class_rows(float* t, const float* table, const int32_t* labels_dev, int32_t B,
                         int32_t dim, int32_t num_classes, srgd_stream_t stream);
@@ -300,6 +332,8 @@ typedef struct srgd_unet_config {
   int32_t channels;        /* 3 */
   int32_t sinu_dim;        /* learned_sinusoidal_dim (32) */
   int32_t num_classes;     /* 3, or 0 for none */
+  int32_t fixed_sinusoidal;/* 0: RandomOrLearnedSinusoidalPosEmb (sinu_dim + 1 features, model.py:596-598);
+                              1: SinusoidalPosEmb(dim) (dim features, model.py:600; the discrete-time family) */
 } srgd_unet_config;
 
 typedef struct srgd_unet srgd_unet;

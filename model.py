@@ -2,10 +2,11 @@
 model.py, backed by the srgd_b200 CUDA library.
 
 Built: the path the shipped configuration selects (conf.model == 'conditional_continuous', reference
-model.py:3503-3515 + 3634-3651: `ConditionalSRUnet` + `ConditionalContinuousTimeGaussianDiffusionSR`) and the
-class-conditional EDM sampler family on the same U-Net (conf.model == 'conditional_elucidated', model.py:3593-3614:
-`ConditionalElucidatedDiffusionSR`).  Other `conf.model` values raise NotImplementedError (the non-conditional
-twins and the discrete DDPM / DDIM family; no configuration or weights ship for them).
+model.py:3503-3515 + 3634-3651: `ConditionalSRUnet` + `ConditionalContinuousTimeGaussianDiffusionSR`) and the two
+other class-conditional sampler families on the same U-Net: EDM (conf.model == 'conditional_elucidated',
+model.py:3593-3614: `ConditionalElucidatedDiffusionSR`) and discrete-time DDPM / DDIM (conf.model ==
+'conditional_gaussian', model.py:3552-3570: `ConditionalGaussianDiffusionSR`).  Other `conf.model` values raise
+NotImplementedError (the non-conditional twins; no configuration or weights ship for them).
 """
 import copy
 import os
@@ -13,11 +14,12 @@ import os
 import torch
 import torch.nn as nn
 
-from srgd_b200 import (ConditionalContinuousTimeGaussianDiffusionSR, ConditionalElucidatedDiffusionSR, ConditionalSRUnet,
-                       alpha_cosine_log_snr, beta_linear_log_snr, get_area, get_coord_and_pad, get_coords)
+from srgd_b200 import (ConditionalContinuousTimeGaussianDiffusionSR, ConditionalElucidatedDiffusionSR,
+                       ConditionalGaussianDiffusionSR, ConditionalSRUnet, alpha_cosine_log_snr, beta_linear_log_snr,
+                       get_area, get_coord_and_pad, get_coords)
 
 __all__ = ["ConditionalSRUnet", "ConditionalContinuousTimeGaussianDiffusionSR", "ConditionalElucidatedDiffusionSR",
-           "get_model", "ModelEma",
+           "ConditionalGaussianDiffusionSR", "get_model", "ModelEma",
            "beta_linear_log_snr", "alpha_cosine_log_snr", "get_coord_and_pad", "get_coords", "get_area",
            "normalize_to_neg_one_to_one", "unnormalize_to_zero_to_one"]
 
@@ -44,13 +46,17 @@ class ModelEma(nn.Module):
 
 
 def get_model(conf, logger):
-    """reference model.py:3500-3666: the shipped conditional_continuous branch (3503-3515, 3634-3651) and the
-    conditional_elucidated branch (EDM sampler family on the same U-Net, 3593-3614)."""
-    if conf.model not in ('conditional_continuous', 'conditional_elucidated'):
+    """reference model.py:3500-3666: the shipped conditional_continuous branch (3503-3515, 3634-3651), the
+    conditional_elucidated branch (EDM sampler family on the same U-Net, 3593-3614) and the conditional_gaussian
+    branch (discrete-time DDPM / DDIM, 3552-3570)."""
+    if conf.model not in ('conditional_continuous', 'conditional_elucidated', 'conditional_gaussian'):
         raise NotImplementedError(
             f"conf.model={conf.model!r}: srgd_b200 builds the class-conditional samplers 'conditional_continuous' "
-            "(shipped) and 'conditional_elucidated' only")
-    assert conf.learned_sinusoidal_cond
+            "(shipped), 'conditional_elucidated' and 'conditional_gaussian' only")
+    if conf.model == 'conditional_gaussian':
+        assert not conf.learned_sinusoidal_cond                                # model.py:3553
+    else:
+        assert conf.learned_sinusoidal_cond
     dim_mults = tuple(int(v) for v in str(conf.ddpm_unet_dim_mults).split(','))
     full_attn = tuple(v.strip() == 'True' for v in str(conf.full_attn).split(','))
     from srgd_b200 import weights as _weights
@@ -58,7 +64,8 @@ def get_model(conf, logger):
     ckpt_path = conf.ckpt_path or None
     # ingest cache: the packed device weights of an earlier start of this checkpoint
     spec = UnetSpec(dim=conf.unet_dim, dim_mults=dim_mults, full_attn=full_attn,
-                    learned_sinusoidal_dim=conf.learned_sinusoidal_dim, num_classes=conf.num_classes)
+                    learned_sinusoidal_dim=conf.learned_sinusoidal_dim, num_classes=conf.num_classes,
+                    learned_sinusoidal_cond=bool(conf.learned_sinusoidal_cond))
     use_cache = bool(ckpt_path) and os.environ.get("SRGD_B200_PACK_CACHE", "1") != "0"
     cached = _weights.load_pack_cache(ckpt_path, spec) if use_cache else None
     unet = ConditionalSRUnet(dim=conf.unet_dim, dim_mults=dim_mults, full_attn=full_attn,
@@ -81,6 +88,16 @@ def get_model(conf, logger):
                     f"num_sample_steps={conf.num_sample_steps}")
         return _finish(conf, logger, diffusion, unet, spec, ckpt_path, use_cache, cached, _weights)
     conf.use_dpmpp_solver = False
+    if conf.model == 'conditional_gaussian':
+        diffusion = ConditionalGaussianDiffusionSR(
+            model=unet, image_size=conf.image_size, timesteps=conf.timesteps,
+            sampling_timesteps=conf.sampling_timesteps, objective=conf.objective, beta_schedule=conf.beta_schedule,
+            offset_noise_strength=conf.offset_noise_strength, min_snr_loss_weight=conf.min_snr_loss_weight,
+            min_snr_gamma=conf.min_snr_gamma, cond_drop_prob=conf.cond_drop_prob,
+            class_cond_drop_prob=conf.class_cond_drop_prob, loss_type=conf.loss_type)
+        logger.info(f"ConditionalGaussianDiffusionSR: image_size={conf.image_size} timesteps={conf.timesteps} "
+                    f"sampling_timesteps={conf.sampling_timesteps}")
+        return _finish(conf, logger, diffusion, unet, spec, ckpt_path, use_cache, cached, _weights)
     diffusion = ConditionalContinuousTimeGaussianDiffusionSR(
         model=unet, image_size=conf.image_size, noise_schedule=conf.noise_schedule,
         num_sample_steps=conf.num_sample_steps, clip_sample_denoised=conf.clip_sample_denoised,

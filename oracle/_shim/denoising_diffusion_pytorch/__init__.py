@@ -8,6 +8,10 @@ from it; on the conditional-continuous hot path only two things survive:
   * `Attend.forward` (see attend.py).
   * for the EDM sampler family (model.py:1731-2600) the `ElucidatedDiffusion` base class
     supplies the preconditioning coefficients and the sigma schedule (restated below, parity unpinned).
+  * for the discrete-time family (model.py:781-1727) the `GaussianDiffusion` base class
+    supplies `device`, `predict_start_from_noise`, `predict_noise_from_start`, `predict_start_from_v`, `q_posterior`
+    and `q_sample` (restated below, parity unpinned); everything else (schedules, buffers) the reference subclass
+    builds itself (model.py:1362-1424).
 Nothing here is product code; it exists so tests/golden/make_golden.py can import the
 UNMODIFIED reference.
 """
@@ -22,8 +26,55 @@ class Unet(nn.Module):
         self.downsample_factor = 2 ** (len(dim_mults) - 1)
 
 
+def _extract(a, t, x_shape):
+    b, *_ = t.shape
+    return a.gather(-1, t).reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
 class GaussianDiffusion(nn.Module):
-    pass
+    """PARITY UNPINNED restatement of what /root/reference/model.py's discrete-time classes inherit from the pip
+    package's `GaussianDiffusion` (denoising_diffusion_pytorch.py of 1.8.15; Ho et al. 2020 eq. 4, 7, 15 and the
+    v-parameterisation of Salimans & Ho 2022): the helpers below read the buffers the reference subclass registers
+    itself (model.py:1395-1424).  Call sites: model.py:1474, 1478, 1483, 1487, 1489 (predict_*), 1499 (q_posterior),
+    1526 / 1581 (q_sample), 1506 / 1521 (device).  The constructor of the real class builds the same buffers again;
+    the subclass overwrites every one of them, so it is reduced to nn.Module bookkeeping here."""
+
+    def __init__(self, model, *, image_size, **kwargs):
+        super().__init__()
+        self.model = model
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (_extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t -
+                _extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+
+    def predict_noise_from_start(self, x_t, t, x0):
+        return ((_extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - x0) /
+                _extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape))
+
+    def predict_v(self, x_start, t, noise):
+        return (_extract(self.sqrt_alphas_cumprod, t, x_start.shape) * noise -
+                _extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * x_start)
+
+    def predict_start_from_v(self, x_t, t, v):
+        return (_extract(self.sqrt_alphas_cumprod, t, x_t.shape) * x_t -
+                _extract(self.sqrt_one_minus_alphas_cumprod, t, x_t.shape) * v)
+
+    def q_posterior(self, x_start, x_t, t):
+        posterior_mean = (_extract(self.posterior_mean_coef1, t, x_t.shape) * x_start +
+                          _extract(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        posterior_variance = _extract(self.posterior_variance, t, x_t.shape)
+        posterior_log_variance_clipped = _extract(self.posterior_log_variance_clipped, t, x_t.shape)
+        return posterior_mean, posterior_variance, posterior_log_variance_clipped
+
+    def q_sample(self, x_start, t, noise=None):
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return (_extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
+                _extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
 
 
 class ElucidatedDiffusion(nn.Module):

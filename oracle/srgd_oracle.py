@@ -42,6 +42,7 @@ class UnetSpec:
     dim_head: int = 32
     full_attn: Tuple[bool, ...] = (False, False, False, True)
     num_classes: Optional[int] = 3
+    learned_sinusoidal_cond: bool = True     # False: fixed SinusoidalPosEmb(dim) (model.py:600; discrete-time family)
 
     @property
     def dims(self):
@@ -93,8 +94,11 @@ def param_shapes(spec: UnetSpec, prefix: str = "model.") -> "OrderedDict[str, Tu
             S[f"{prefix}{name}.to_out.1.g"] = (1, c, 1, 1)
 
     conv("init_conv", spec.dim, 2 * spec.channels, 7)                     # model.py:583
-    S[f"{prefix}time_mlp.0.weights"] = (spec.learned_sinusoidal_dim // 2,)  # model.py:231
-    linear("time_mlp.1", td, spec.learned_sinusoidal_dim + 1)             # model.py:605
+    if spec.learned_sinusoidal_cond:
+        S[f"{prefix}time_mlp.0.weights"] = (spec.learned_sinusoidal_dim // 2,)  # model.py:231
+        linear("time_mlp.1", td, spec.learned_sinusoidal_dim + 1)         # model.py:598, 605
+    else:
+        linear("time_mlp.1", td, spec.dim)                                # model.py:600-601, 605
     linear("time_mlp.3", td, td)
     if spec.num_classes is not None:                                      # model.py:612-619
         S[f"{prefix}class_mlp.0.weight"] = (spec.num_classes, spec.dim)
@@ -254,9 +258,16 @@ def _pixel_shuffle_upsample(sd, p, x):
 
 def time_embedding(sd, spec: UnetSpec, time, class_label=None, prefix="model."):
     """model.py:223-238 + 603-608 (time_mlp) and 612-619 + 692-694 (class_mlp)."""
-    x = time.reshape(-1, 1).float()
-    freqs = x * sd[prefix + "time_mlp.0.weights"][None, :] * 2 * math.pi
-    f = torch.cat((x, freqs.sin(), freqs.cos()), dim=-1)
+    if spec.learned_sinusoidal_cond:
+        x = time.reshape(-1, 1).float()
+        freqs = x * sd[prefix + "time_mlp.0.weights"][None, :] * 2 * math.pi
+        f = torch.cat((x, freqs.sin(), freqs.cos()), dim=-1)
+    else:                                                                 # SinusoidalPosEmb, model.py:209-221
+        half_dim = spec.dim // 2
+        emb = math.log(10000) / (half_dim - 1)
+        emb = torch.exp(torch.arange(half_dim, device=time.device) * -emb)
+        emb = time.reshape(-1)[:, None] * emb[None, :]
+        f = torch.cat((emb.sin(), emb.cos()), dim=-1)
     t = F.linear(f, sd[prefix + "time_mlp.1.weight"], sd[prefix + "time_mlp.1.bias"])
     t = F.linear(F.gelu(t), sd[prefix + "time_mlp.3.weight"], sd[prefix + "time_mlp.3.bias"])
     if class_label is not None:
@@ -728,3 +739,172 @@ def edm_tiled_sample(sd, spec, p: EdmParams, batch_size, condition_x, class_labe
             images[:, :, stop:sbottom, sleft:sright] = cropped
     top, bottom, left, right = ts["crop"]
     return (images[:, :, top:bottom, left:right].clamp(-1., 1.) + 1) * 0.5
+
+
+# --------------------------------------------------------------------------------------------
+# Discrete-time sampler family on the same U-Net: ConditionalGaussianDiffusionSR,
+# model.py:1311-1660 -- DDPM ancestral sampling and DDIM.  The schedules and buffers are the reference's own code
+# (model.py:744-777, 1362-1424: pinned by the goldens); `predict_start_from_noise`, `predict_noise_from_start`,
+# `predict_start_from_v`, `q_posterior` and `q_sample` come from the absent pip base class `GaussianDiffusion`
+# (denoising-diffusion-pytorch==1.8.15) and are restated from the published algebra: PARITY UNPINNED at that
+# boundary.  tests/golden/gauss_tiny.npz (tests/golden/make_golden_gauss.py) pins the rest against the unmodified
+# reference class running on the same restated base (oracle/_shim).
+# --------------------------------------------------------------------------------------------
+
+def gauss_betas(schedule: str, timesteps: int) -> torch.Tensor:
+    """model.py:744-777 (float64)."""
+    if schedule == "linear":
+        scale = 1000 / timesteps
+        return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64)
+    steps = timesteps + 1
+    t = torch.linspace(0, timesteps, steps, dtype=torch.float64) / timesteps
+    if schedule == "cosine":
+        ac = torch.cos((t + 0.008) / (1 + 0.008) * math.pi * 0.5) ** 2
+    elif schedule == "sigmoid":
+        start, end, tau = -3, 3, 1
+        v_start, v_end = torch.tensor(start / tau).sigmoid(), torch.tensor(end / tau).sigmoid()
+        ac = (-((t * (end - start) + start) / tau).sigmoid() + v_end) / (v_end - v_start)
+    else:
+        raise ValueError(f"unknown beta schedule {schedule}")
+    ac = ac / ac[0]
+    return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+
+
+@dataclass(frozen=True)
+class GaussParams:
+    timesteps: int = 1000
+    sampling_timesteps: int = 250
+    objective: str = "pred_noise"
+    beta_schedule: str = "linear"
+    ddim_sampling_eta: float = 0.
+
+
+def gauss_tables(p: GaussParams) -> Dict[str, torch.Tensor]:
+    """The registered fp32 buffers, model.py:1371-1424."""
+    betas = gauss_betas(p.beta_schedule, p.timesteps)
+    alphas = 1. - betas
+    ac = torch.cumprod(alphas, dim=0)
+    ac_prev = F.pad(ac[:-1], (1, 0), value=1.)
+    pv = betas * (1. - ac_prev) / (1. - ac)
+    T = dict(betas=betas, alphas_cumprod=ac, alphas_cumprod_prev=ac_prev, sqrt_alphas_cumprod=torch.sqrt(ac),
+             sqrt_one_minus_alphas_cumprod=torch.sqrt(1. - ac), sqrt_recip_alphas_cumprod=torch.sqrt(1. / ac),
+             sqrt_recipm1_alphas_cumprod=torch.sqrt(1. / ac - 1), posterior_variance=pv,
+             posterior_log_variance_clipped=torch.log(pv.clamp(min=1e-20)),
+             posterior_mean_coef1=betas * torch.sqrt(ac_prev) / (1. - ac),
+             posterior_mean_coef2=(1. - ac_prev) * torch.sqrt(alphas) / (1. - ac))
+    return {k: v.to(torch.float32) for k, v in T.items()}
+
+
+def _gx(a, t, x):
+    """extract, model.py:730-733"""
+    return a.to(x.device).gather(-1, t).reshape(t.shape[0], *((1,) * (x.ndim - 1)))
+
+
+def gauss_model_predictions(sd, spec, p: GaussParams, T, x, t, condition_x=None, class_label=None, cond_scale=1.0,
+                            class_cond_scale=1.0, clip_x_start=False, rederive_pred_noise=False):
+    """model.py:1449-1489 -> (pred_noise, x_start)."""
+    if (cond_scale != 1.0) and (class_cond_scale != 1.0):
+        raise NotImplementedError("Currently, you cannot specify both cond_scale and class_cond_scale at the same time.")
+    net = lambda lab, cond: unet_forward(sd, spec, x, t, lab, cond)
+    if cond_scale == 1.0 and class_cond_scale == 1.0:
+        out = net(class_label, condition_x)
+    elif cond_scale != 1.0:
+        cond_out, null_out = net(class_label, condition_x), net(class_label, None)
+        out = null_out + (cond_out - null_out) * cond_scale
+    else:
+        cond_out, null_out = net(class_label, condition_x), net(None, condition_x)
+        out = null_out + (cond_out - null_out) * class_cond_scale
+    clip = (lambda v: torch.clamp(v, min=-1., max=1.)) if clip_x_start else (lambda v: v)
+    from_start = lambda x0: (_gx(T["sqrt_recip_alphas_cumprod"], t, x) * x - x0) / _gx(T["sqrt_recipm1_alphas_cumprod"], t, x)
+    if p.objective == "pred_noise":
+        pred_noise = out
+        x_start = clip(_gx(T["sqrt_recip_alphas_cumprod"], t, x) * x - _gx(T["sqrt_recipm1_alphas_cumprod"], t, x) * out)
+        if clip_x_start and rederive_pred_noise:
+            pred_noise = from_start(x_start)
+    elif p.objective == "pred_x0":
+        x_start = clip(out)
+        pred_noise = from_start(x_start)
+    else:
+        x_start = clip(_gx(T["sqrt_alphas_cumprod"], t, x) * x - _gx(T["sqrt_one_minus_alphas_cumprod"], t, x) * out)
+        pred_noise = from_start(x_start)
+    return pred_noise, x_start
+
+
+def gauss_p_sample(sd, spec, p: GaussParams, T, x, t: int, condition_x, class_label, cond_scale=1.0,
+                   class_cond_scale=1.0, noise=None, generator=None):
+    """model.py:1491-1514 -> (pred_img, x_start).  `noise` overrides the randn_like draw (teacher-forced tests)."""
+    bt = torch.full((x.shape[0],), t, device=x.device, dtype=torch.long)
+    _, x_start = gauss_model_predictions(sd, spec, p, T, x, bt, condition_x, class_label, cond_scale, class_cond_scale)
+    x_start = x_start.clamp(-1., 1.)
+    mean = _gx(T["posterior_mean_coef1"], bt, x) * x_start + _gx(T["posterior_mean_coef2"], bt, x) * x
+    log_var = _gx(T["posterior_log_variance_clipped"], bt, x)
+    if noise is None:
+        noise = torch.randn(x.shape, generator=generator, device=x.device) if t > 0 else 0.
+    elif t == 0:
+        noise = 0.
+    return mean + (0.5 * log_var).exp() * noise, x_start
+
+
+def gauss_ddim_step(sd, spec, p: GaussParams, T, img, time: int, time_next: int, condition_x, class_label,
+                    cond_scale=1.0, class_cond_scale=1.0, noise=None, generator=None):
+    """One iteration of ddim_sample's loop, model.py:1599-1622 -> (img, x_start)."""
+    tc = torch.full((img.shape[0],), time, device=img.device, dtype=torch.long)
+    pred_noise, x_start = gauss_model_predictions(sd, spec, p, T, img, tc, condition_x, class_label, cond_scale,
+                                                  class_cond_scale, clip_x_start=True, rederive_pred_noise=True)
+    if time_next < 0:
+        return x_start, x_start
+    alpha, alpha_next = T["alphas_cumprod"][time], T["alphas_cumprod"][time_next]
+    sigma = p.ddim_sampling_eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+    c = (1 - alpha_next - sigma ** 2).sqrt()
+    if noise is None:
+        noise = torch.randn(img.shape, generator=generator, device=img.device)
+    return x_start * alpha_next.sqrt() + c * pred_noise + sigma * noise, x_start
+
+
+def gauss_sample(sd, spec, p: GaussParams, batch_size, condition_x, class_label=None, cond_scale=1.0,
+                 guidance_start_steps=0, class_cond_scale=1.0, class_guidance_start_steps=0, generation_start_steps=0,
+                 num_sample_steps=None, model_steps=None, generator=None):
+    """sample -> p_sample_loop (sampling_timesteps == timesteps) or ddim_sample, model.py:1517-1660.  `model_steps`
+    (optional list) receives the state after every step; draws come from `generator` (default: torch's global CPU
+    generator) in the reference's order."""
+    T = gauss_tables(p)
+    S = p.sampling_timesteps if num_sample_steps is None else num_sample_steps
+    _n, _c, h, w = condition_x.shape
+    condition_x = condition_x * 2 - 1
+    shape = (batch_size, spec.channels, h, w)
+
+    def start(target_time):
+        if generation_start_steps > 0:
+            t = torch.tensor([target_time] * batch_size, device=condition_x.device).long()
+            noise = torch.randn(condition_x.shape, generator=generator, device=condition_x.device)
+            return (_gx(T["sqrt_alphas_cumprod"], t, condition_x) * condition_x +
+                    _gx(T["sqrt_one_minus_alphas_cumprod"], t, condition_x) * noise)            # q_sample (pip, unpinned)
+        return torch.randn(shape, generator=generator, device=condition_x.device)
+
+    def scales(i):
+        return (1.0 if i < guidance_start_steps else cond_scale,
+                1.0 if i < class_guidance_start_steps else class_cond_scale)
+
+    if p.sampling_timesteps >= p.timesteps:                                   # is_ddim_sampling False, model.py:1388
+        img = start(p.timesteps - generation_start_steps)
+        for i, t in enumerate(reversed(range(0, p.timesteps))):
+            if i < generation_start_steps:
+                continue
+            cs, ccs = scales(i)
+            img, _ = gauss_p_sample(sd, spec, p, T, img, t, condition_x, class_label, cs, ccs, generator=generator)
+            if model_steps is not None:
+                model_steps.append(img.clone())
+        return (img + 1) * 0.5
+    times = torch.linspace(-1, p.timesteps - 1, steps=S + 1)
+    times = list(reversed(times.int().tolist()))
+    pairs = list(zip(times[:-1], times[1:]))
+    img = start(pairs[generation_start_steps][0] if generation_start_steps > 0 else 0)
+    for i, (time, time_next) in enumerate(pairs):
+        if i < generation_start_steps:
+            continue
+        cs, ccs = scales(i)
+        img, _ = gauss_ddim_step(sd, spec, p, T, img, time, time_next, condition_x, class_label, cs, ccs,
+                                 generator=generator)
+        if model_steps is not None:
+            model_steps.append(img.clone())
+    return (img + 1) * 0.5

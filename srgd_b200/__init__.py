@@ -8,12 +8,13 @@ from .arch import UnetSpec, unet_keys
 from .diffusion import (ConditionalContinuousTimeGaussianDiffusionSR, alpha_cosine_log_snr,
                         beta_linear_log_snr)
 from .edm import ConditionalElucidatedDiffusionSR
+from .gaussian import ConditionalGaussianDiffusionSR
 from .sharding import gather_rows, sample_sharded, shard_counts, shard_range
 from .tiling import TilePlan, get_area, get_coord_and_pad, get_coords
 from .unet import ConditionalSRUnet
 
 __all__ = ["UnetSpec", "unet_keys", "ConditionalSRUnet", "ConditionalContinuousTimeGaussianDiffusionSR",
-           "ConditionalElucidatedDiffusionSR",
+           "ConditionalElucidatedDiffusionSR", "ConditionalGaussianDiffusionSR",
            "beta_linear_log_snr", "alpha_cosine_log_snr", "TilePlan", "get_coord_and_pad", "get_coords",
            "get_area", "shard_range", "shard_counts", "gather_rows", "sample_sharded"]
 __version__ = "0.1.0"

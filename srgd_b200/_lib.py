@@ -33,6 +33,16 @@ class EdmScalars(C.Structure):
                 ("step", C.c_float), ("c_in_next", C.c_float), ("clip", C.c_int32)]
 
 
+class GaussScalars(C.Structure):
+    _fields_ = [("objective", C.c_int32), ("mode", C.c_int32), ("clip", C.c_int32), ("rederive", C.c_int32),
+                ("guidance_scale", C.c_float), ("sqrt_recip_ac", C.c_float), ("sqrt_recipm1_ac", C.c_float),
+                ("sqrt_ac", C.c_float), ("sqrt_1m_ac", C.c_float), ("coef1", C.c_float), ("coef2", C.c_float),
+                ("noise_scale", C.c_float), ("sqrt_ac_next", C.c_float), ("c", C.c_float)]
+
+
+OBJ_PRED_NOISE, OBJ_PRED_X0, OBJ_PRED_V = 0, 1, 2
+GAUSS_DDPM, GAUSS_DDIM, GAUSS_DDIM_LAST = 0, 1, 2
+
 SRGD_MAX_TILES_PER_CALL = 64
 
 
@@ -62,7 +72,7 @@ class UnetConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("n_stages", C.c_int32), ("dim_mults", C.c_int32 * 6),
                 ("full_attn", C.c_int32 * 6), ("heads", C.c_int32), ("dim_head", C.c_int32),
                 ("groups", C.c_int32), ("channels", C.c_int32), ("sinu_dim", C.c_int32),
-                ("num_classes", C.c_int32)]
+                ("num_classes", C.c_int32), ("fixed_sinusoidal", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -79,6 +89,7 @@ SIGNATURES = {
     "srgd_edm_perturb": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _I64, _P]),
     "srgd_edm_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(EdmScalars), _P]),
     "srgd_edm_dpmpp": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _I64, _P]),
+    "srgd_gauss_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(GaussScalars), _P]),
     "srgd_q_sample": (C.c_int, [_P, _P, _P, _I64, C.c_float, C.c_float, _P]),
     "srgd_finalize_image": (C.c_int, [_P, _P, _I64, _P]),
     "srgd_gather_tiles": (C.c_int, [_P, _P, C.POINTER(TileCoords), _I32, _I32, _I32, _I32, _P]),
@@ -107,6 +118,7 @@ SIGNATURES = {
     "srgd_final_conv": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "srgd_dense_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "srgd_fourier_features": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "srgd_sinusoidal_pos_emb": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "srgd_add_class_rows": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
     "srgd_unet_param_count": (C.c_int, [C.POINTER(UnetConfig)]),
     "srgd_unet_param_name": (C.c_char_p, [C.POINTER(UnetConfig), C.c_int]),

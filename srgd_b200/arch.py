@@ -18,6 +18,9 @@ class UnetSpec:
     dim_head: int = 32
     full_attn: Tuple[bool, ...] = (False, False, False, True)
     num_classes: Optional[int] = 3
+    # True: RandomOrLearnedSinusoidalPosEmb on log-SNR / c_noise (continuous-time and EDM families, model.py:596-598);
+    # False: the fixed SinusoidalPosEmb(dim) on integer timesteps (discrete-time family, model.py:600)
+    learned_sinusoidal_cond: bool = True
 
     @property
     def widths(self) -> List[int]:
@@ -67,8 +70,11 @@ def unet_keys(spec: UnetSpec) -> Dict[str, Tuple[int, ...]]:
     n = len(spec.dim_mults)
     k["init_conv.weight"] = (spec.dim, 2 * spec.channels, 7, 7)
     k["init_conv.bias"] = (spec.dim,)
-    k["time_mlp.0.weights"] = (spec.learned_sinusoidal_dim // 2,)
-    k["time_mlp.1.weight"] = (td, spec.learned_sinusoidal_dim + 1)
+    if spec.learned_sinusoidal_cond:
+        k["time_mlp.0.weights"] = (spec.learned_sinusoidal_dim // 2,)
+        k["time_mlp.1.weight"] = (td, spec.learned_sinusoidal_dim + 1)
+    else:                                            # SinusoidalPosEmb has no parameters; fourier_dim = dim
+        k["time_mlp.1.weight"] = (td, spec.dim)
     k["time_mlp.1.bias"] = (td,)
     k["time_mlp.3.weight"] = (td, td)
     k["time_mlp.3.bias"] = (td,)

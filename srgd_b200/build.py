@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsrgd_b200.so")
-SOURCES = ["api.cu", "sampler.cu", "edm.cu", "conv_igemm.cu", "norm.cu", "attention.cu", "attention_tc.cu", "linattn_fused.cu", "linattn_pp.cu", "embed.cu", "unet.cu"]
+SOURCES = ["api.cu", "sampler.cu", "edm.cu", "gaussian.cu", "conv_igemm.cu", "norm.cu", "attention.cu", "attention_tc.cu", "linattn_fused.cu", "linattn_pp.cu", "embed.cu", "unet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

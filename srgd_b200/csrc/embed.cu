@@ -2,6 +2,7 @@
 //   pack_input        : cat(x, x_self_cond) (model.py:681-684) -> bf16 row-im2col for the 7x7 init conv
 //   final_conv        : final 1x1 conv C -> 3 writing fp32 NCHW eps (model.py:675, 725)
 //   fourier_features  : RandomOrLearnedSinusoidalPosEmb (model.py:233-238)
+//   sinusoidal_pos_emb: SinusoidalPosEmb (model.py:209-221), the time embedding of the discrete-time family
 //   dense_rows        : nn.Linear on a handful of rows with SiLU / GELU on the input
 //                       (time_mlp 603-608, class_mlp 612-619, ResnetBlock.mlp 264-267)
 //   add_class_rows    : t = t + class_mlp(label) (model.py:692-694)
@@ -117,6 +118,18 @@ __global__ void fourier_features_kernel(const float* __restrict__ log_snr, const
   out[i] = v;
 }
 
+// emb = t * freq[k]  (x[:, None] * emb[None, :], model.py:219);  out = [sin(emb) | cos(emb)]  (model.py:220)
+__global__ void sinusoidal_pos_emb_kernel(const float* __restrict__ t, const float* __restrict__ freq,
+                                          float* __restrict__ out, int B, int half) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int width = 2 * half;
+  if (i >= B * width) return;
+  const int b = i / width, j = i % width;
+  const float e = __fmul_rn(t[b], freq[j % half]);
+  out[i] = j < half ? sinf(e) : cosf(e);
+}
+
 __device__ __forceinline__ float act_in(float v, int act) {
   if (act == 1) return v / (1.0f + expf(-v));                               // SiLU
   if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); // exact GELU (nn.GELU default)
@@ -213,6 +226,19 @@ extern "C" int srgd_fourier_features(const float* log_snr, const float* weights,
   ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
   SRGD_CUDA_OK(launch_k(fourier_features_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), log_snr,
                         weights, out, B, half_dim));
+  count_launch();
+  return SRGD_OK;
+}
+
+extern "C" int srgd_sinusoidal_pos_emb(const float* t, const float* freq, float* out, int32_t B, int32_t half_dim,
+                                       srgd_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  SRGD_REQUIRE(t && freq && out && B > 0 && half_dim > 0, "sinusoidal_pos_emb: bad arguments");
+  const int total = B * 2 * half_dim;
+  ProfScope prof(SRGD_PK_OTHER, 0.0, 0.0, as_stream(stream));
+  SRGD_CUDA_OK(launch_k(sinusoidal_pos_emb_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), t, freq,
+                        out, B, half_dim));
   count_launch();
   return SRGD_OK;
 }

@@ -225,7 +225,8 @@ static int validate_cfg(const srgd_unet_config* c) {
   SRGD_REQUIRE(c->heads == 4 && c->dim_head == 32, "unet: only heads=4, dim_head=32 is built");
   SRGD_REQUIRE(c->groups == 8, "unet: only resnet_block_groups=8 is built");
   SRGD_REQUIRE(c->channels == 3, "unet: only channels=3 is built");
-  SRGD_REQUIRE(c->sinu_dim > 0 && c->sinu_dim % 2 == 0, "unet: bad learned_sinusoidal_dim");
+  SRGD_REQUIRE(c->fixed_sinusoidal == 0 || c->fixed_sinusoidal == 1, "unet: bad fixed_sinusoidal flag");
+  SRGD_REQUIRE(c->fixed_sinusoidal || (c->sinu_dim > 0 && c->sinu_dim % 2 == 0), "unet: bad learned_sinusoidal_dim");
   for (int i = 0; i < c->n_stages; ++i) SRGD_REQUIRE(c->dim_mults[i] >= 1, "unet: bad dim_mults");
   return SRGD_OK;
 }
@@ -485,14 +486,15 @@ static int forward_impl(srgd_unet& u, Arena& ar, bool dry, const float* x, const
   }
 
   // ---- embeddings (model.py:689-694 and every ResnetBlock.mlp, 264-267/277-279) ----
-  const int fdim = c.sinu_dim + 1;
+  const int fdim = c.fixed_sinusoidal ? c.dim : c.sinu_dim + 1;         // model.py:596-601
   float* feats = reinterpret_cast<float*>(f.alloc((size_t)B * fdim * 4));
   float* t1 = reinterpret_cast<float*>(f.alloc((size_t)B * td * 4));
   float* t = reinterpret_cast<float*>(f.alloc((size_t)B * td * 4));
   float* ss = reinterpret_cast<float*>(f.alloc((size_t)B * u.ss_total * 4));
   f.ss = ss;
   if (!dry && f.ok()) {
-    f.run(srgd_fourier_features(log_snr, u.time_freq, feats, B, c.sinu_dim / 2, st));
+    if (c.fixed_sinusoidal) f.run(srgd_sinusoidal_pos_emb(log_snr, u.time_freq, feats, B, c.dim / 2, st));
+    else f.run(srgd_fourier_features(log_snr, u.time_freq, feats, B, c.sinu_dim / 2, st));
     f.run(srgd_dense_rows(feats, u.time_w1, u.time_b1, t1, B, td, fdim, 0, 0, st));
     f.run(srgd_dense_rows(t1, u.time_w2, u.time_b2, t, B, td, td, 2, 0, st));
     if (labels != nullptr && u.class_table != nullptr)

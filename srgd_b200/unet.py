@@ -64,11 +64,9 @@ class ConditionalSRUnet(nn.Module):
         if out_dim not in (None, channels): unsupported.append("out_dim")
         if not self_condition: unsupported.append("self_condition=False")
         if learned_variance: unsupported.append("learned_variance=True")
-        if not (learned_sinusoidal_cond or random_fourier_features):
-            unsupported.append("fixed sinusoidal time embedding")
         if not pixel_shuffle_upsample: unsupported.append("pixel_shuffle_upsample=False")
         if unsupported:
-            raise NotImplementedError("srgd_b200 builds the shipped conditional_continuous U-Net only; unsupported: "
+            raise NotImplementedError("srgd_b200 builds the class-conditional U-Net of the shipped configuration; unsupported: "
                                       + ", ".join(unsupported))
         if isinstance(full_attn, bool):
             full_attn = (full_attn,) * len(dim_mults)
@@ -76,12 +74,13 @@ class ConditionalSRUnet(nn.Module):
         self.spec = UnetSpec(dim=dim, dim_mults=tuple(int(m) for m in dim_mults), channels=channels,
                              groups=resnet_block_groups, learned_sinusoidal_dim=learned_sinusoidal_dim,
                              heads=attn_heads, dim_head=attn_dim_head, full_attn=tuple(bool(f) for f in full_attn),
-                             num_classes=num_classes)
+                             num_classes=num_classes,
+                             learned_sinusoidal_cond=bool(learned_sinusoidal_cond or random_fourier_features))
         self.channels = channels
         self.self_condition = self_condition
         self.num_classes = num_classes
         self.out_dim = channels
-        self.random_or_learned_sinusoidal_cond = True
+        self.random_or_learned_sinusoidal_cond = self.spec.learned_sinusoidal_cond         # model.py:594
         self.downsample_factor = self.spec.downsample_factor
         gen = torch.Generator().manual_seed(0)
         for name, shape in unet_keys(self.spec).items():

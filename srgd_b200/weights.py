@@ -34,6 +34,7 @@ def make_config(spec: UnetSpec) -> _lib.UnetConfig:
     cfg.heads, cfg.dim_head, cfg.groups = spec.heads, spec.dim_head, spec.groups
     cfg.channels, cfg.sinu_dim = spec.channels, spec.learned_sinusoidal_dim
     cfg.num_classes = int(spec.num_classes or 0)
+    cfg.fixed_sinusoidal = 0 if spec.learned_sinusoidal_cond else 1
     return cfg
 
 
@@ -78,7 +79,13 @@ def pack(spec: UnetSpec, sd: Dict[str, torch.Tensor], device: torch.device) -> D
     wi[:, :, :42] = w.permute(0, 2, 3, 1).reshape(o, 7, 42)     # (ky, kx, c) -> column kx*6 + c
     out["init.w"] = bf(wi.reshape(o, 7 * 64))
     out["init.b"] = f32(g("init_conv.bias"))
-    out["time.freq"] = f32(g("time_mlp.0.weights"))
+    if spec.learned_sinusoidal_cond:
+        out["time.freq"] = f32(g("time_mlp.0.weights"))
+    else:
+        # SinusoidalPosEmb's frequency table with the reference's own ops (model.py:216-218), on the host
+        half = spec.dim // 2
+        emb = math.log(10000) / (half - 1)
+        out["time.freq"] = torch.exp(torch.arange(half) * -emb).to(device=device, dtype=torch.float32).contiguous()
     out["time.w1"], out["time.b1"] = f32(g("time_mlp.1.weight")), f32(g("time_mlp.1.bias"))
     out["time.w2"], out["time.b2"] = f32(g("time_mlp.3.weight")), f32(g("time_mlp.3.bias"))
 
@@ -177,7 +184,8 @@ def _ckpt_identity(ckpt_path: str) -> Dict[str, int]:
 
 def _spec_key(spec: UnetSpec) -> str:
     return repr((spec.dim, tuple(spec.dim_mults), spec.channels, spec.groups, spec.learned_sinusoidal_dim, spec.heads,
-                 spec.dim_head, tuple(spec.full_attn), spec.num_classes))
+                 spec.dim_head, tuple(spec.full_attn), spec.num_classes) +
+                (() if spec.learned_sinusoidal_cond else ("fixed_sinusoidal",)))
 
 
 def save_pack_cache(ckpt_path: str, spec: UnetSpec, packed: Dict[str, torch.Tensor]) -> Optional[str]:

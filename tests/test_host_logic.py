@@ -37,9 +37,12 @@ def test_struct_layouts_match_header(tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu %zu ", sizeof(srgd_step_scalars), sizeof(srgd_conv_src), sizeof(srgd_conv_phase),
          sizeof(srgd_conv_desc), sizeof(srgd_unet_config));
-  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(srgd_conv_desc, srcs), offsetof(srgd_conv_desc, phases),
+  printf("%zu %zu %zu %zu %zu %zu ", offsetof(srgd_conv_desc, srcs), offsetof(srgd_conv_desc, phases),
          offsetof(srgd_conv_desc, weight), offsetof(srgd_conv_desc, act), offsetof(srgd_conv_desc, gn_partials),
          offsetof(srgd_unet_config, heads));
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(srgd_edm_scalars), sizeof(srgd_gauss_scalars),
+         offsetof(srgd_gauss_scalars, guidance_scale), offsetof(srgd_gauss_scalars, c),
+         offsetof(srgd_unet_config, fixed_sinusoidal));
   return 0;
 }''')
     exe = tmp_path / "probe"
@@ -47,7 +50,9 @@ int main(void) {
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     D, U = _lib.ConvDesc, _lib.UnetConfig
     want = [C.sizeof(_lib.StepScalars), C.sizeof(_lib.ConvSrc), C.sizeof(_lib.ConvPhase), C.sizeof(D), C.sizeof(U),
-            D.srcs.offset, D.phases.offset, D.weight.offset, D.act.offset, D.gn_partials.offset, U.heads.offset]
+            D.srcs.offset, D.phases.offset, D.weight.offset, D.act.offset, D.gn_partials.offset, U.heads.offset,
+            C.sizeof(_lib.EdmScalars), C.sizeof(_lib.GaussScalars), _lib.GaussScalars.guidance_scale.offset,
+            _lib.GaussScalars.c.offset, U.fixed_sinusoidal.offset]
     assert got == want
 
 
@@ -305,3 +310,49 @@ def test_get_model_builds_the_edm_family(tmp_path):
     assert s.shape == (9,) and abs(float(s[0]) - 60.0) < 1e-4 and float(s[-1]) == 0.0 and abs(float(s[-2]) - 0.002) < 1e-6
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         edm.sample(batch_size=1, condition_x=torch.rand(1, 3, 64, 64), num_sample_steps=4)
+
+
+def test_get_model_builds_the_discrete_time_family(tmp_path):
+    """conf.model == 'conditional_gaussian' (model.py:3552-3570): the U-Net with the fixed SinusoidalPosEmb (no
+    `time_mlp.0.weights`, a dim-wide first time-MLP layer), the reference's 13 registered buffers in front of the
+    `model.` keys, strict checkpoint round trip, and the per-step scalars of DDPM / DDIM against the oracle's tables."""
+    import logging
+    import config as Cfg
+    import model as M
+    yaml_path = tmp_path / "c.yaml"
+    yaml_path.write_text("model: conditional_gaussian\nunet_dim: 64\nimage_size: 64\nlearned_sinusoidal_cond: false\n"
+                         "timesteps: 1000\nsampling_timesteps: 10\nobjective: pred_v\nbeta_schedule: sigmoid\n")
+    conf = Cfg.load_config(str(yaml_path))
+    spec = O.UnetSpec(dim=64, learned_sinusoidal_cond=False)
+    p = O.GaussParams(1000, 10, "pred_v", "sigmoid")
+    tab = O.gauss_tables(p)
+    sd = dict(tab)
+    sd["log_one_minus_alphas_cumprod"] = torch.log(1. - torch.cumprod(1. - O.gauss_betas("sigmoid", 1000), 0)).float()
+    snr = torch.cumprod(1. - O.gauss_betas("sigmoid", 1000), 0)
+    snr = snr / (1 - snr)
+    sd["loss_weight"] = (snr / (snr + 1)).float()
+    sd.update(O.make_state_dict(spec, 5, prefix="model."))
+    ck = tmp_path / "w.pth"
+    torch.save({"ema_model": sd}, ck)
+    conf.ckpt_path = str(ck)
+    m = M.get_model(conf, logging.getLogger("t")).module
+    assert isinstance(m, M.ConditionalGaussianDiffusionSR) and m.is_ddim_sampling and m.num_timesteps == 1000
+    assert not m.model.random_or_learned_sinusoidal_cond
+    got = m.state_dict()
+    assert set(got) == set(sd) and list(got)[:3] == ["betas", "alphas_cumprod", "alphas_cumprod_prev"]
+    assert all(torch.equal(got[k], v) for k, v in sd.items())
+    assert "model.time_mlp.0.weights" not in got and got["model.time_mlp.1.weight"].shape == (256, 64)
+    # DDIM scalars (model.py:1608-1612) with the oracle's arithmetic
+    m.ddim_sampling_eta = 0.7
+    s = m._scalars(600, _lib.GAUSS_DDIM, True, True, 2.0, 300)
+    a, an = tab["alphas_cumprod"][600], tab["alphas_cumprod"][300]
+    sigma = 0.7 * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+    assert s.noise_scale == float(sigma) and s.c == float((1 - an - sigma ** 2).sqrt()) and s.sqrt_ac_next == float(an.sqrt())
+    assert s.objective == _lib.OBJ_PRED_V and s.sqrt_ac == float(tab["sqrt_alphas_cumprod"][600])
+    s = m._scalars(17, _lib.GAUSS_DDPM, True, False, 1.0)
+    assert s.noise_scale == float((0.5 * tab["posterior_log_variance_clipped"][17]).exp())
+    assert s.coef1 == float(tab["posterior_mean_coef1"][17]) and s.coef2 == float(tab["posterior_mean_coef2"][17])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.sample(batch_size=1, condition_x=torch.rand(1, 3, 64, 64))
+    with pytest.raises(ValueError, match="unknown beta schedule"):
+        M.ConditionalGaussianDiffusionSR(m.model, image_size=64, beta_schedule="quadratic")

@@ -202,3 +202,43 @@ def test_edm_family_oracle_vs_reference_golden(golden_dir):
                                               tile_size=32, tile_stride=32, generator=gen()), T(g["tiled_heun"]))
         assert torch.equal(O.edm_sample_dpmpp(sd, spec, p, 2, cond, label, class_cond_scale=2.0, num_sample_steps=n,
                                               generator=gen()), T(g["dpmpp_class"]))
+
+
+def test_gaussian_family_oracle_vs_reference_golden(golden_dir):
+    """the oracle's restatement of ConditionalGaussianDiffusionSR (model.py:1311-1660) against
+    outputs of the unmodified reference class (tests/golden/make_golden_gauss.py): the U-Net with the fixed
+    SinusoidalPosEmb, the registered buffers of every beta schedule, model_predictions for every objective, p_sample,
+    a full DDPM loop and two DDIM runs (eta 0 / 0.7, both guidance kinds, generation_start_steps) -- bit-exact.
+    (The five pip base-class helpers behind both are the shim's restatement: parity unpinned.)"""
+    g = _load(golden_dir, "gauss_tiny")
+    spec = O.UnetSpec(dim=16, learned_sinusoidal_cond=False)
+    sd = O.make_state_dict(spec, 11, prefix="model.")
+    assert "model.time_mlp.0.weights" not in sd and sd["model.time_mlp.1.weight"].shape == (64, 16)
+    cond, x, label = T(g["cond"]), T(g["x"]), T(g["label"])
+    gen = lambda: torch.Generator().manual_seed(71)
+    lin = O.GaussParams(1000, 6, "pred_noise", "linear")
+    with torch.inference_mode():
+        assert torch.equal(O.unet_forward(sd, spec, x, torch.tensor([7, 500]), label, cond * 2 - 1), T(g["unet"]))
+        tab = O.gauss_tables(lin)
+        for name in ("betas", "alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_log_variance_clipped",
+                     "posterior_mean_coef1", "posterior_mean_coef2"):
+            assert torch.equal(tab[name], T(g["linear_" + name])), name
+        t400 = torch.full((2,), 400, dtype=torch.long)
+        for obj, sched in (("pred_noise", "linear"), ("pred_x0", "cosine"), ("pred_v", "sigmoid")):
+            p = O.GaussParams(1000, 6, obj, sched)
+            tb = O.gauss_tables(p)
+            assert torch.equal(tb["alphas_cumprod"], T(g[sched + "_alphas_cumprod"])), sched
+            pn, x0 = O.gauss_model_predictions(sd, spec, p, tb, x, t400, cond * 2 - 1, label, 1.0, 2.0,
+                                               clip_x_start=True, rederive_pred_noise=True)
+            assert torch.equal(pn, T(g[obj + "_noise"])) and torch.equal(x0, T(g[obj + "_x0"])), obj
+        img, x0 = O.gauss_p_sample(sd, spec, lin, tab, x, 500, cond * 2 - 1, label, 1.5, 1.0, generator=gen())
+        assert torch.equal(img, T(g["p_sample_500"])) and torch.equal(x0, T(g["p_sample_500_x0"]))
+        assert torch.equal(O.gauss_p_sample(sd, spec, lin, tab, x, 0, cond * 2 - 1, label)[0], T(g["p_sample_0"]))
+        assert torch.equal(O.gauss_sample(sd, spec, O.GaussParams(8, 8, "pred_x0", "cosine"), 2, cond, label,
+                                          class_cond_scale=2.0, class_guidance_start_steps=3, generator=gen()),
+                           T(g["ddpm_x0_cosine"]))
+        assert torch.equal(O.gauss_sample(sd, spec, O.GaussParams(1000, 6, "pred_v", "sigmoid"), 2, cond, label,
+                                          class_cond_scale=2.0, generator=gen()), T(g["ddim_v_sigmoid"]))
+        assert torch.equal(O.gauss_sample(sd, spec, O.GaussParams(1000, 6, "pred_noise", "linear", 0.7), 2, cond, label,
+                                          cond_scale=1.5, generation_start_steps=2, generator=gen()),
+                           T(g["ddim_eps_eta"]))
