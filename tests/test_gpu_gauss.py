@@ -82,7 +82,12 @@ def test_predictions_and_p_sample_teacher_forced(objective, schedule):
         print(f"{objective}/{schedule} t={t} cs={cs} ccs={ccs}: img {e_img:.5f} x0 {e_x0:.5f} pred_noise {e_pn:.5f} (x{amp:.1f})")
         # at t = 0 the posterior mean IS x_start (coef1 = 1); with pred_x0 that is the raw network output
         assert e_img <= (3e-2 if (objective == "pred_x0" and t == 0) else 1e-2)
-        assert float((x0c - r_x0c).abs().max()) <= 5e-2 and e_pn <= 5e-2 * max(1.0, amp)
+        # x_start = x / sqrt(ac) - sqrt(1/ac - 1) * eps amplifies the network error at large t for pred_noise (the
+        # rederived noise divides it out again); the other objectives amplify on the way to pred_noise instead
+        recipm1 = float(tab["sqrt_recipm1_alphas_cumprod"][t])
+        x0_tol = 3e-2 * max(1.0, recipm1) if objective == "pred_noise" else 5e-2
+        pn_tol = 5e-2 if objective == "pred_noise" else 5e-2 * max(1.0, amp)
+        assert float((x0c - r_x0c).abs().max()) <= x0_tol and e_pn <= pn_tol
     with pytest.raises(NotImplementedError):
         m.p_sample(x, 5, cond, label, 2.0, 2.0)
 
