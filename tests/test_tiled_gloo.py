@@ -85,11 +85,24 @@ def _product_path(sd, shard, max_rows=64):
     return (img[:, :, top:bottom, left:right].clamp(-1, 1) + 1) * 0.5
 
 
+_memo = {}
+
+
 def _reference(sd):
-    cond01, label = _inputs()
-    gen = torch.Generator().manual_seed(71)
-    return O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, num_sample_steps=STEPS, tile_size=TILE,
-                          tile_stride=TILE, generator=gen)
+    """The oracle's image for the fixed inputs and weights of this file (computed once per process)."""
+    if "ref" not in _memo:
+        cond01, label = _inputs()
+        gen = torch.Generator().manual_seed(71)
+        _memo["ref"] = O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, num_sample_steps=STEPS,
+                                      tile_size=TILE, tile_stride=TILE, generator=gen)
+    return _memo["ref"]
+
+
+def _single_exact(sd):
+    """The single-process exact-mode image (computed once per process)."""
+    if "exact" not in _memo:
+        _memo["exact"] = _product_path(sd, shard=True, max_rows=64)
+    return _memo["exact"]
 
 
 def _free_port():
@@ -122,7 +135,7 @@ def test_run_tiled_exact_mode_single_process():
     differs from the reference's minibatch partition only by the CPU conv's batch-dependent blocking (<= 5e-4)."""
     torch.set_num_threads(2)
     sd = O.make_state_dict(SPEC, 11)
-    a = _product_path(sd, shard=True, max_rows=64)
+    a = _single_exact(sd)
     b = _product_path(sd, shard=True, max_rows=3)
     assert torch.equal(a, b)
     torch.testing.assert_close(a, _reference(sd), rtol=0, atol=5e-4)
@@ -134,7 +147,7 @@ def test_run_tiled_sharded_over_gloo_is_bit_identical(world):
     replica ends with the single-process exact-mode image, bit for bit."""
     torch.set_num_threads(2)
     sd = O.make_state_dict(SPEC, 11)
-    single = _product_path(sd, shard=True)
+    single = _single_exact(sd)
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
