@@ -1,6 +1,6 @@
 """compute-sanitizer driver (not a pytest test): two p_sample steps of a dim-64 U-Net on a 128x64 tile batch of 2 with
 classifier-free guidance -- every kernel family of the hot path (both conv kernels incl. the halo variant is skipped at
-this width, fused linear attention, tcgen05 flash attention, GroupNorm apply with folded statistics, sampler update; round 2: split-K conv tiles, class-guidance sharing, staged LinearAttention stores, the EDM kernels).
+this width, fused linear attention, tcgen05 flash attention, GroupNorm apply with folded statistics, sampler update; round 2: split-K conv tiles, class-guidance sharing, staged LinearAttention stores, the EDM kernels, the discrete-time family's embedding + update kernels).
 
     compute-sanitizer --tool memcheck  python tests/gpu_sanitize.py
     compute-sanitizer --tool racecheck python tests/gpu_sanitize.py
@@ -43,6 +43,21 @@ def main():
                            class_cond_scale=2.0, num_sample_steps=2)
     torch.cuda.synchronize()
     print("edm:", float(y.mean()), flush=True)
+    if os.environ.get("SAN_GAUSS", "1") == "1":
+        # the discrete-time family: fixed sinusoidal time embedding + the fused DDPM / DDIM update (small U-Net)
+        spec_g = O.UnetSpec(dim=64, learned_sinusoidal_cond=False)
+        unet_g = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=False, num_classes=3)
+        gd = M.ConditionalGaussianDiffusionSR(unet_g, image_size=64, timesteps=1000, sampling_timesteps=2,
+                                              objective="pred_v", ddim_sampling_eta=0.5)
+        gd.load_state_dict(O.make_state_dict(spec_g, 5), strict=False)
+        gd = gd.eval().to("cuda:0")
+        gd.progress = False
+        with torch.inference_mode():
+            c64 = torch.rand(2, 3, 64, 64, generator=g).cuda()
+            z = gd.sample(batch_size=2, condition_x=c64, class_label=torch.tensor([1], device="cuda"), class_cond_scale=2.0)
+            z2, _ = gd.p_sample(z * 2 - 1, 500, c64 * 2 - 1, torch.tensor([1], device="cuda"), 1.5, 1.0)
+        torch.cuda.synchronize()
+        print("gauss:", float(z.mean()), float(z2.mean()), flush=True)
     print("sanitize run finished:", float(x.abs().mean()), diff.last_step_launches, "launches per step")
 
 
