@@ -300,9 +300,14 @@ struct Fwd {
   // conv3x3 whose epilogue leaves the GroupNorm partial records in `part` (debug paths: statistics in `stats`)
   void conv_gn(const void* a0, int c0, const void* a1, int c1, int H, int W, const void* w, const float* bias, int cout,
                void* out, float* part, float* stats) {
-    conv(a0, c0, a1, c1, H, W, 3, w, bias, cout, out, part, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC);
-    if (!dry && ok() && (conv_impl & 3)) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
+    const bool fused = fused_stats(H, W);
+    conv(a0, c0, a1, c1, H, W, 3, w, bias, cout, out, fused ? part : nullptr, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC);
+    if (!dry && ok() && !fused) run(srgd_groupnorm_stats(out, stats, B, H, W, cout, st));
   }
+  // The conv epilogue's partial records describe at most 4 samples per 128-pixel tile: feature maps below 32 pixels
+  // (inputs under ~48x48 at four levels; the reference accepts anything divisible by 8, model.py:679) take the
+  // stand-alone statistics kernel instead.
+  bool fused_stats(int H, int W) const { return !(conv_impl & 3) && H * W >= 32; }
 
   // A conv whose second source has only Bb < B rows (the same rows for every group of Bb samples: init_conv's output
   // shared by the two halves of a class-guidance batch): B / Bb launches over Bb samples each.  The GroupNorm partial
@@ -333,13 +338,13 @@ struct Fwd {
   void* resblock(const ResP& r, const void* xa, const void* xb, int H, int W, float* inv_out = nullptr,
                  float* eps_out = nullptr, int Ba = -1, int Bb = -1) {
     const size_t M = (size_t)B * H * W;
-    const bool fused_stats = !(conv_impl & 3);
+    const bool fused = fused_stats(H, W);
     const bool shared_in = Ba > 0 && Ba < B, bcast_b = Bb > 0 && Bb < B;
     void* c1 = alloc(M * r.cout * 2);
     float* stats = reinterpret_cast<float*>(alloc((size_t)B * 8 * 2 * sizeof(float)));
     float* part = reinterpret_cast<float*>(alloc((size_t)srgd_conv_m_tiles(B, H, W) * 8 * 2 * sizeof(float)));
-    const float* st_arg = fused_stats ? nullptr : stats;
-    const float* pt_arg = fused_stats ? part : nullptr;
+    const float* st_arg = fused ? nullptr : stats;
+    const float* pt_arg = fused ? part : nullptr;
     if (shared_in) {
       void* c1s = alloc((size_t)Ba * H * W * r.cout * 2);
       conv(xa, r.cin0, nullptr, 0, H, W, 3, r.c1_w, r.c1_b, r.cout, c1s, part, nullptr, nullptr, 0, SRGD_OUT_BF16_NHWC,
@@ -617,8 +622,6 @@ static int check_shape(const srgd_unet* u, int B, int H, int W) {
   SRGD_REQUIRE(B > 0 && H > 0 && W > 0, "unet: bad shape");
   SRGD_REQUIRE(H % factor == 0 && W % factor == 0,
                "your input dimensions (%d, %d) need to be divisible by %d, given the unet", H, W, factor);
-  SRGD_REQUIRE((H / factor) * (W / factor) >= 32,
-               "unet: the coarsest feature map must have at least 32 pixels (input %dx%d too small)", H, W);
   return SRGD_OK;
 }
 

@@ -22,6 +22,7 @@ from oracle import srgd_oracle as O  # noqa: E402  (checker only)
 from srgd_b200 import _lib  # noqa: E402
 from srgd_b200.tiled import CudaTiledOps, run_tiled  # noqa: E402
 from srgd_b200.tiling import TilePlan  # noqa: E402
+import model as M  # noqa: E402
 from test_gpu_unet import _oracle_on_gpu, make_diffusion  # noqa: E402
 
 _models = {}
@@ -166,3 +167,66 @@ def test_config4_canvas_teacher_forced_vs_oracle(first):
         print(f"2304x2304 canvas step {i} ccs {ccs}: next-canvas max-abs {err:.5f}")
         assert err <= 1e-2, (i, err)
         img = ref
+
+
+RAGGED = [(1, 8, 8), (3, 40, 72), (2, 24, 136), (5, 104, 88), (1, 264, 200), (7, 16, 16), (2, 8, 1024), (2, 40, 40), (3, 24, 24)]
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+def test_unet_ragged_shapes_vs_oracle(dim):
+    """The reference's only shape rule is H, W divisible by 8 (model.py:679).  Smallest legal input, odd batch sizes,
+    non-square and non-power-of-two extents, widths that are no multiple of the conv tiles (128 / 256 pixels) nor of
+    the LinearAttention tiles: eps against the fp32 oracle on the GPU, row by row the same tolerance as the goldens."""
+    from test_gpu_unet import _oracle_on_gpu
+    spec = O.UnetSpec(dim=dim)
+    sd = O.make_state_dict(spec, 77, init="torch")
+    unet = M.ConditionalSRUnet(dim=dim, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=64, num_sample_steps=250)
+    diff.load_state_dict(sd, strict=True)
+    diff = diff.eval().to("cuda")
+    gsd = _oracle_on_gpu(sd)
+    g = torch.Generator().manual_seed(2)
+    for B, H, W in RAGGED:
+        x = torch.randn(B, 3, H, W, generator=g).cuda()
+        cond = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).cuda()
+        lsnr = (torch.rand(B, generator=g) * 16 - 8).cuda()
+        lab = torch.randint(0, 3, (B,), generator=g).cuda()
+        got = diff.model(x, lsnr, lab, cond)
+        with torch.inference_mode():
+            ref = O.unet_forward(gsd, spec, x, lsnr, lab, cond)
+        err = (got - ref).abs()
+        print(f"dim {dim} B={B} {H}x{W}: eps max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f} "
+              f"(ref rms {float(ref.pow(2).mean().sqrt()):.3f})")
+        assert got.shape == (B, 3, H, W)
+        assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2, (B, H, W)
+    with pytest.raises(AssertionError):
+        diff.model(torch.zeros(1, 3, 12, 64, device="cuda"), torch.zeros(1, device="cuda"))
+
+
+def test_unet_other_architectures_vs_oracle():
+    """Constructor options the reference exposes and get_model forwards (model.py:3503-3515): three resolution levels
+    instead of four, full attention at two levels, no class conditioning."""
+    from test_gpu_unet import _oracle_on_gpu
+    g = torch.Generator().manual_seed(4)
+    for kw in (dict(dim_mults=(1, 2, 4), full_attn=(False, False, True), num_classes=3),
+               dict(dim_mults=(1, 2, 4, 8), full_attn=(False, False, True, True), num_classes=3),
+               dict(dim_mults=(1, 2, 4, 8), full_attn=(False, False, False, True), num_classes=None),
+               dict(dim_mults=(1, 1, 2, 2, 4), full_attn=(False, False, False, False, True), num_classes=3)):
+        spec = O.UnetSpec(dim=64, **kw)
+        sd = O.make_state_dict(spec, 31, init="torch")
+        unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, **kw)
+        diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=64, num_sample_steps=250)
+        diff.load_state_dict(sd, strict=True)
+        diff = diff.eval().to("cuda")
+        gsd = _oracle_on_gpu(sd)
+        H = W = 64
+        x = torch.randn(2, 3, H, W, generator=g).cuda()
+        cond = (torch.rand(2, 3, H, W, generator=g) * 2 - 1).cuda()
+        lsnr = torch.tensor([-3.0, 4.0]).cuda()
+        lab = None if kw["num_classes"] is None else torch.tensor([2, 0]).cuda()
+        got = diff.model(x, lsnr, lab, cond)
+        with torch.inference_mode():
+            ref = O.unet_forward(gsd, spec, x, lsnr, lab, cond)
+        err = (got - ref).abs()
+        print(f"{kw}: eps max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f}")
+        assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2, kw
