@@ -375,9 +375,15 @@ class ConditionalElucidatedDiffusionSR(nn.Module):
                 x_hat = ops.gather(images_hat, chunk, tile_size)
                 x_in = ops.gather(xin_canvas, chunk, tile_size)
                 nxt, x0 = self._heun(x_hat, x_in, sigma_hat, sigma_next, cond_tiles[key], class_label, cs, ccs, clamp)
-                ops.scatter(images, chunk, nxt, tile_size)
-                if x_start is not None:
-                    ops.scatter(x_start, chunk, x0, tile_size)
+                if plan.disjoint:
+                    ops.scatter(images, chunk, nxt, tile_size)
+                    if x_start is not None:
+                        ops.scatter(x_start, chunk, x0, tile_size)
+                else:                # overlapping tiles (tile_stride < tile_size): the later tile wins (model.py:2436)
+                    for j, c in enumerate(chunk):
+                        ops.scatter(images, [c], nxt[j:j + 1], tile_size)
+                        if x_start is not None:
+                            ops.scatter(x_start, [c], x0[j:j + 1], tile_size)
             if i % 2 == 1:
                 # get_noised_images(zeros, i), model.py:2448: sigma_i of the DEFAULT schedule (self.num_sample_steps)
                 fresh = self._randn(shape, dev)

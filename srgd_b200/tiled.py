@@ -147,6 +147,10 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
     generator before each image (inference.py:81).  The tiles of a call are stacked image-major into one denoiser
     batch of at most `max_rows` rows, so the 4-tile odd steps of a small image still fill the GPU."""
     tile = plan.tile_size
+    if shard and not plan.disjoint:
+        raise ValueError("shard_tiles (exact mode) regroups the tiles of a step into different denoiser calls, which is "
+                         "only equivalent for disjoint tiles: use tile_stride == tile_size with a tile size that divides "
+                         "the 256-aligned canvas, or the default mode")
     world = dist.get_world_size(group) if (shard and dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     dev = img.device
@@ -160,10 +164,16 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
             return ops.gather(canvas[lo:lo + 1], chunk, tile)
         return torch.cat([ops.gather(canvas[k:k + 1], chunk, tile) for k in range(lo, hi)], 0)
 
+    disjoint = plan.disjoint
+
     def scatter_all(canvas, coords, stack):                # stack: [n_img * len(coords), ...] image-major
         n = len(coords)
         for k in range(n_img):
-            ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
+            if disjoint:
+                ops.scatter(canvas[k:k + 1], coords, stack[k * n:(k + 1) * n], tile)
+            else:                                          # overlapping tiles: the later tile wins, as in the
+                for j, c in enumerate(coords):             # reference's sequential slice assignments (model.py:3383)
+                    ops.scatter(canvas[k:k + 1], [c], stack[k * n + j:k * n + j + 1], tile)
 
     def denoise(i, parity, slot, chunk, noise, cs, ccs, emit):
         """One group of tiles `chunk` for all images, in calls of at most max_rows rows; emit(lo, hi, out, x0) receives
@@ -204,6 +214,13 @@ def run_tiled(ops, img: torch.Tensor, cond_canvas: torch.Tensor, plan: TilePlan,
                     # [n_img * len(chunk), ...] image-major
                     outs.append((chunk, got[0][0] if len(got) == 1 else torch.cat([g[0] for g in got], 0),
                                  got[0][1] if len(got) == 1 else torch.cat([g[1] for g in got], 0)))
+                    if not disjoint:
+                        # overlapping tiles (tile_stride < tile_size): the reference advances the canvas in place,
+                        # so the next minibatch must see this one's pixels (model.py:3374-3385)
+                        scatter_all(img, *outs[-1][:2])
+                        if x_start is not None:
+                            scatter_all(x_start, outs[-1][0], outs[-1][2])
+                        outs.pop()
                 for chunk, out, x0 in outs:
                     scatter_all(img, chunk, out)
                     if x_start is not None:

@@ -64,6 +64,20 @@ class TilePlan:
         self.grids: List[List[Tuple[int, int]]] = [[(c[0], c[2]) for c in aligned], [(c[0], c[2]) for c in shifted]]
         self.tile_size = tile_size
 
+    @property
+    def disjoint(self) -> bool:
+        """True if no two tiles of a grid overlap (tile_stride == tile_size on the 256-aligned canvas).  With a smaller
+        stride, or a tile size that does not divide the canvas (the last tile is pulled back to the border), later
+        tiles of a step read pixels earlier minibatches of the same step have already advanced (the reference updates
+        the canvas in place, model.py:3374-3385): the result then depends on the minibatch partition."""
+        t = self.tile_size
+        for grid in self.grids:
+            for k, (y, x) in enumerate(grid):
+                for (y2, x2) in grid[k + 1:]:
+                    if abs(y - y2) < t and abs(x - x2) < t:
+                        return False
+        return True
+
     def tiles_per_image(self, num_steps: int) -> int:
         even = (num_steps + 1) // 2
         return even * len(self.grids[0]) + (num_steps - even) * len(self.grids[1])

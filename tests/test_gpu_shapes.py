@@ -230,3 +230,61 @@ def test_unet_other_architectures_vs_oracle():
         err = (got - ref).abs()
         print(f"{kw}: eps max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f}")
         assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2, kw
+
+
+def test_tiled_sample_overlapping_tiles_vs_oracle():
+    """tile_size 128 with tile_stride 64 (the shifted grid's 25 tiles overlap; the canvas advances in place minibatch by
+    minibatch and the later tile of a minibatch wins, model.py:3374-3385) and tile_size 192 (does not divide the
+    512-pixel canvas: the last tile of each axis is pulled back), both sampler families that have a tiled loop;
+    exact mode refuses such plans."""
+    from test_gpu_unet import _oracle_on_gpu
+    spec = O.UnetSpec(dim=64)
+    sd = O.make_state_dict(spec, 22, init="torch")
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=128, num_sample_steps=12)
+    diff.load_state_dict(sd, strict=True)
+    diff = diff.eval().to("cuda")
+    diff.progress = False
+    gsd = _oracle_on_gpu(sd)
+    g = torch.Generator().manual_seed(14)
+    cond01 = torch.rand(1, 3, 200, 264, generator=g).cuda()
+    label = torch.tensor([2]).cuda()
+    for tile, stride in ((128, 64), (192, 192)):
+        torch.manual_seed(71)
+        img = diff.tiled_sample(batch_size=6, tile_size=tile, tile_stride=stride, condition_x=cond01, class_label=label,
+                                class_cond_scale=2.0, num_sample_steps=12)
+        torch.manual_seed(71)
+        with torch.inference_mode():
+            ref = O.tiled_sample(gsd, spec, 6, cond01, label, class_cond_scale=2.0, num_sample_steps=12, tile_size=tile,
+                                 tile_stride=stride)
+        p = G.psnr(img.cpu(), ref.cpu())
+        print(f"tiled_sample tile {tile} stride {stride}: PSNR {p:.2f} dB, max-abs {float((img - ref).abs().max()):.4f}")
+        assert img.shape == (1, 3, 200, 264) and p >= 45.0
+        # the last 10 steps of the full schedule from the same noised condition (generation_start_steps): the noise
+        # amplification of the first steps is out of the picture and the per-step bar applies
+        kw = dict(class_cond_scale=2.0, num_sample_steps=250, generation_start_steps=240)
+        torch.manual_seed(71)
+        img = diff.tiled_sample(batch_size=6, tile_size=tile, tile_stride=stride, condition_x=cond01, class_label=label, **kw)
+        torch.manual_seed(71)
+        with torch.inference_mode():
+            ref = O.tiled_sample(gsd, spec, 6, cond01, label, tile_size=tile, tile_stride=stride, **kw)
+        err = float((img - ref).abs().max())
+        print(f"  last 10 of 250 steps: max-abs {err:.5f}")
+        assert err <= 1e-2
+        with pytest.raises(ValueError, match="disjoint"):
+            diff.tiled_sample(batch_size=6, tile_size=tile, tile_stride=stride, condition_x=cond01, class_label=label,
+                              num_sample_steps=2, shard_tiles=True)
+    # the EDM family's tiled loop (reads images_hat, writes images: only the write order matters there)
+    edm = M.ConditionalElucidatedDiffusionSR(unet, image_size=128, num_sample_steps=8).eval().to("cuda")
+    edm.progress = False
+    gsd_e = {("net." + k[len("model."):]): v for k, v in gsd.items()}
+    torch.manual_seed(71)
+    img = edm.tiled_sample(batch_size=6, tile_size=128, tile_stride=64, condition_x=cond01, class_label=label,
+                           class_cond_scale=2.0, num_sample_steps=8)
+    torch.manual_seed(71)
+    with torch.inference_mode():
+        ref = O.edm_tiled_sample(gsd_e, spec, O.EdmParams(), 6, cond01, label, class_cond_scale=2.0, num_sample_steps=8,
+                                 tile_size=128, tile_stride=64)
+    p = G.psnr(img.cpu(), ref.cpu())
+    print(f"EDM tiled_sample tile 128 stride 64: PSNR {p:.2f} dB")
+    assert p >= 45.0

@@ -242,3 +242,18 @@ def test_gaussian_family_oracle_vs_reference_golden(golden_dir):
         assert torch.equal(O.gauss_sample(sd, spec, O.GaussParams(1000, 6, "pred_noise", "linear", 0.7), 2, cond, label,
                                           cond_scale=1.5, generation_start_steps=2, generator=gen()),
                            T(g["ddim_eps_eta"]))
+
+
+def test_tiled_sample_with_overlapping_tiles(golden_dir):
+    """tile_stride < tile_size and tile sizes / strides that do not divide the canvas (tests/golden/make_golden_stride.py,
+    unmodified reference): the oracle's in-place, minibatch-by-minibatch canvas update reproduces the reference."""
+    g = _load(golden_dir, "tiled_stride_tiny")
+    spec = O.UnetSpec(dim=16)
+    sd = O.make_state_dict(spec, 11)
+    cond01 = torch.rand(1, 3, 104, 120, generator=torch.Generator().manual_seed(7))
+    assert abs(float(cond01.double().sum()) - float(g["cond01_checksum"])) < 1e-6
+    with torch.inference_mode():
+        for name, (tile, stride) in {"t32_s16": (32, 16), "t64_s48": (64, 48), "t48_s48": (48, 48)}.items():
+            got = O.tiled_sample(sd, spec, 5, cond01, torch.tensor([1]), class_cond_scale=2.0, num_sample_steps=3,
+                                 tile_size=tile, tile_stride=stride, generator=torch.Generator().manual_seed(71))
+            torch.testing.assert_close(got, T(g[name]), rtol=0, atol=5e-4, msg=name)

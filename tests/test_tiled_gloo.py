@@ -65,20 +65,20 @@ def _inputs():
     return cond01, torch.tensor([1])
 
 
-def _product_path(sd, shard, max_rows=64):
+def _product_path(sd, shard, max_rows=64, stride=TILE, tile=TILE, nsteps=STEPS):
     """What ConditionalContinuousTimeGaussianDiffusionSR.tiled_sample does around run_tiled, on CPU tensors."""
     cond01, label = _inputs()
     gen = torch.Generator().manual_seed(71)
     cond = cond01 * 2 - 1
-    plan = TilePlan(cond.shape[2], cond.shape[3], TILE, TILE)
+    plan = TilePlan(cond.shape[2], cond.shape[3], tile, stride)
     cond = F.pad(cond, plan.canvas_pad, mode="reflect")
     img = torch.randn(cond.shape, generator=gen)
     it, ib, il, ir = plan.inner
     cond_canvas = torch.zeros_like(cond)
     cond_canvas[:, :, it:ib, il:ir] = cond[:, :, it:ib, il:ir]
-    steps = torch.linspace(1., 0., STEPS + 1)
+    steps = torch.linspace(1., 0., nsteps + 1)
     ops = TorchOps(sd, gen, row_by_row=shard)
-    img, _ = run_tiled(ops, img, cond_canvas, plan, steps, STEPS, BATCH, label, 1.0, 0, 2.0, 0, 0,
+    img, _ = run_tiled(ops, img, cond_canvas, plan, steps, nsteps, BATCH, label, 1.0, 0, 2.0, 0, 0,
                        shard=shard, max_rows=max_rows)
     assert ops.invariant_calls == ([True, False] if shard else [])      # switched on for the loop, restored after
     top, bottom, left, right = plan.crop
@@ -96,6 +96,26 @@ def _reference(sd):
         _memo["ref"] = O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, num_sample_steps=STEPS,
                                       tile_size=TILE, tile_stride=TILE, generator=gen)
     return _memo["ref"]
+
+
+def test_overlapping_tiles_follow_the_reference_partition_and_refuse_exact_mode():
+    """tile_stride < tile_size: the shifted grid's tiles overlap and the reference advances the canvas in place,
+    minibatch by minibatch (model.py:3374-3385).  The default mode keeps that partition and equals the oracle bit for
+    bit; exact mode would regroup the calls and is refused."""
+    torch.set_num_threads(2)
+    sd = O.make_state_dict(SPEC, 11)
+    cond01, label = _inputs()
+    ref = O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, num_sample_steps=3, tile_size=64,
+                         tile_stride=48, generator=torch.Generator().manual_seed(71))
+    assert torch.equal(_product_path(sd, shard=False, stride=48, tile=64, nsteps=3), ref)
+    with pytest.raises(ValueError, match="disjoint"):
+        _product_path(sd, shard=True, stride=48, tile=64, nsteps=3)
+    # a tile size that does not divide the canvas: the last tile of each axis is pulled back and overlaps its neighbour
+    ref = O.tiled_sample(sd, SPEC, BATCH, cond01, label, class_cond_scale=2.0, num_sample_steps=3, tile_size=48,
+                         tile_stride=48, generator=torch.Generator().manual_seed(71))
+    assert torch.equal(_product_path(sd, shard=False, stride=48, tile=48, nsteps=3), ref)
+    with pytest.raises(ValueError, match="disjoint"):
+        _product_path(sd, shard=True, stride=48, tile=48, nsteps=3)
 
 
 def _single_exact(sd):
