@@ -203,6 +203,14 @@ def current_stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def require_like(t, ref, what: str):
+    """A caller-supplied tensor that a kernel reads element for element next to `ref` (torch would raise a broadcast
+    / size error in the reference's elementwise op; a raw pointer would be read out of bounds)."""
+    if tuple(t.shape) != tuple(ref.shape) or t.device != ref.device:
+        raise RuntimeError(f"{what}: expected a tensor of shape {tuple(ref.shape)} on {ref.device}, "
+                           f"got {tuple(t.shape)} on {t.device}")
+
+
 def require_cuda(t, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: tensor is on {t.device}; srgd_b200 runs on sm_100 CUDA devices only "

@@ -179,6 +179,8 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
             return self._update(x, eps_c, eps_n, None, s)
         if noise is None:
             noise = self._randn(x.shape, x.device)                              # model.py:3187
+        else:
+            _lib.require_like(noise, x, "p_sample noise")
         return self._update(x, eps_c, eps_n, noise.contiguous().float(), s)
 
     # ---------------------------------------------------------------------------------------
@@ -187,6 +189,8 @@ class ConditionalContinuousTimeGaussianDiffusionSR(nn.Module):
     def q_sample(self, x_start, times, noise=None, return_alpha_sigma_sum=False):
         if noise is None:
             noise = self._randn(x_start.shape, x_start.device)
+        else:
+            _lib.require_like(noise, x_start, "q_sample noise")
         times_t = times if torch.is_tensor(times) else torch.tensor(times)
         log_snr = self.log_snr(times_t.float())
         if x_start.is_cuda and log_snr.numel() == 1:

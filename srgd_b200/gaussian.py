@@ -219,6 +219,8 @@ class ConditionalGaussianDiffusionSR(nn.Module):
         """sqrt_alphas_cumprod[t] * x_start + sqrt_one_minus_alphas_cumprod[t] * noise."""
         if noise is None:
             noise = self._randn(x_start.shape, x_start.device)                              # randn_like(x_start)
+        else:
+            _lib.require_like(noise, x_start, "q_sample noise")
         tt = t.reshape(-1) if torch.is_tensor(t) else torch.tensor([int(t)])
         if x_start.is_cuda and (tt.numel() == 1 or bool((tt == tt[0]).all())):
             tab, k = self._tables(), int(tt[0])
@@ -323,6 +325,8 @@ class ConditionalGaussianDiffusionSR(nn.Module):
         s = self._scalars(k, _lib.GAUSS_DDPM, True, False, scale)
         if k > 0 and noise is None:
             noise = self._randn(x.shape, x.device)                                          # model.py:1512
+        elif noise is not None:
+            _lib.require_like(noise, x, "p_sample noise")
         img, x0, _ = self._update(x, out_c, out_n, noise.contiguous().float() if k > 0 else None, s)
         return img, x0
 

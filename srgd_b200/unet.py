@@ -251,14 +251,29 @@ class ConditionalSRUnet(nn.Module):
             cond: Optional[torch.Tensor], rows: int, n_cond_rows: int, out: Optional[torch.Tensor] = None):
         """eps[rows,3,H,W]; row b reads x[b % Bx] / cond[b % Bx] (cond only for b < n_cond_rows) with
         label labels_i32[b] (<0 = null) and log_snr[b].  rows = Bx, or 2*Bx for the CFG pair."""
+        # the reference fails in torch.cat((x, x_self_cond), dim=1) / the init conv for these (model.py:684-686); here
+        # they would be out-of-bounds reads of the raw pointers
+        if x.ndim != 4 or x.shape[1] != self.channels:
+            raise RuntimeError(f"expected x of shape [B, {self.channels}, H, W], got {tuple(x.shape)}")
+        assert all(d % self.downsample_factor == 0 for d in x.shape[-2:]), \
+            f'your input dimensions {x.shape[-2:]} need to be divisible by {self.downsample_factor}, given the unet'
+        if cond is not None and tuple(cond.shape) != tuple(x.shape):
+            raise RuntimeError(f"Sizes of tensors must match: x {tuple(x.shape)} vs condition {tuple(cond.shape)}")
+        if cond is not None and cond.device != x.device:
+            raise RuntimeError(f"Expected all tensors to be on the same device, got {x.device} and {cond.device}")
+        if rows not in (x.shape[0], 2 * x.shape[0]):
+            raise RuntimeError(f"rows={rows} must be the batch of x ({x.shape[0]}) or twice that (guidance pair)")
+        if log_snr.numel() != rows or (labels_i32 is not None and labels_i32.numel() != rows):
+            raise RuntimeError(f"time has {log_snr.numel()} entries"
+                               + ("" if labels_i32 is None else f", class_label {labels_i32.numel()}")
+                               + f" for a batch of {rows}")
         _lib.require_cuda(x, "ConditionalSRUnet")
         Bx, _, H, W = x.shape
         self._ensure_handle(x.device)
         x = x.contiguous().float()
         if cond is not None:
             cond = cond.contiguous().float()
-        log_snr = log_snr.contiguous().float()
-        assert log_snr.numel() == rows and (labels_i32 is None or labels_i32.numel() == rows)
+        log_snr = log_snr.to(x.device).contiguous().float()
         if out is None:
             out = torch.empty(rows, self.channels, H, W, device=x.device, dtype=torch.float32)
         lib = _lib.load()

@@ -112,6 +112,14 @@ def test_input_validation():
     with pytest.raises(NotImplementedError):
         diff.p_sample(torch.zeros(1, 3, 64, 64, device="cuda"), torch.tensor(1.0), None, None, 2.0, 2.0,
                       torch.tensor(0.9))
+    # through the sampler wrappers too: the divisibility assert (model.py:679) and mismatched condition sizes
+    with pytest.raises(AssertionError):
+        diff.p_sample(torch.zeros(1, 3, 60, 64, device="cuda"), torch.tensor(0.5), None, None, 1.0, 1.0, torch.tensor(0.4))
+    with pytest.raises(RuntimeError, match="must match"):
+        diff.p_sample(torch.zeros(2, 3, 64, 64, device="cuda"), torch.tensor(0.5), torch.zeros(2, 3, 32, 32, device="cuda"),
+                      None, 1.0, 1.0, torch.tensor(0.4))
+    with pytest.raises(RuntimeError, match="must match"):
+        diff.sample(batch_size=2, condition_x=torch.rand(1, 3, 64, 64, device="cuda"), num_sample_steps=2)
 
 
 def test_p_sample_teacher_forced_vs_reference_golden():

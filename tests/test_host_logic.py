@@ -356,3 +356,23 @@ def test_get_model_builds_the_discrete_time_family(tmp_path):
         m.sample(batch_size=1, condition_x=torch.rand(1, 3, 64, 64))
     with pytest.raises(ValueError, match="unknown beta schedule"):
         M.ConditionalGaussianDiffusionSR(m.model, image_size=64, beta_schedule="quadratic")
+
+
+def test_unet_shape_errors_come_before_any_device_work():
+    """Mismatched inputs fail in the reference inside torch.cat / the init conv / the divisibility assert
+    (model.py:679-686); here they must be caught on the host, because the C side reads raw pointers."""
+    import model as M
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    x, t = torch.zeros(2, 3, 64, 64), torch.zeros(2)
+    with pytest.raises(RuntimeError, match="must match"):
+        unet(x, t, None, torch.zeros(2, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="must match"):
+        unet(x, t, None, torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="expected x of shape"):
+        unet(torch.zeros(2, 1, 64, 64), t)
+    with pytest.raises(AssertionError, match="divisible by 8"):
+        unet(torch.zeros(2, 3, 60, 64), t)
+    with pytest.raises(RuntimeError, match="for a batch of"):
+        unet(x, torch.zeros(3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unet(x, t)
