@@ -61,7 +61,7 @@ def seed_everything(seed):
 
 def _to_unit_tensor(image: Image.Image) -> torch.Tensor:
     """PIL RGB -> float [1,3,H,W] in [0,1] (what torchvision's ToTensor does for uint8 images)."""
-    arr = np.asarray(image, dtype=np.uint8)
+    arr = np.array(image, dtype=np.uint8)          # a writable copy (torch warns about read-only arrays)
     return torch.from_numpy(arr).permute(2, 0, 1).unsqueeze(0).float().div(255.)
 
 
