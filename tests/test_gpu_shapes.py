@@ -318,3 +318,22 @@ def test_unet_130_row_batch_agrees_with_small_batches():
     err = (big[idx] - ref).abs()
     print(f"rows 0 / 129 vs oracle: max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f}")
     assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 512, 512), (2, 768, 1280), (1, 1024, 1024)])
+def test_unet_large_single_tiles_vs_oracle(B, H, W):
+    """`sample()` on inputs larger than the CLI's 256-pixel tiles (the reference accepts any image_size): up to 1024x1024
+    in one U-Net call -- a million-pixel LinearAttention, 16384-token full attention at the coarsest level."""
+    diff, gsd, spec = full_model("torch")
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(B, 3, H, W, generator=g).cuda()
+    cond = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).cuda()
+    lsnr = (torch.rand(B, generator=g) * 16 - 8).cuda()
+    lab = torch.randint(0, 3, (B,), generator=g).cuda()
+    got = diff.model(x, lsnr, lab, cond)
+    with torch.inference_mode():
+        ref = torch.cat([O.unet_forward(gsd, spec, x[k:k + 1], lsnr[k:k + 1], lab[k:k + 1], cond[k:k + 1])
+                         for k in range(B)], 0)
+    err = (got - ref).abs()
+    print(f"B={B} {H}x{W}: eps max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f}")
+    assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2
