@@ -70,13 +70,12 @@ class TilePlan:
         stride, or a tile size that does not divide the canvas (the last tile is pulled back to the border), later
         tiles of a step read pixels earlier minibatches of the same step have already advanced (the reference updates
         the canvas in place, model.py:3374-3385): the result then depends on the minibatch partition."""
-        t = self.tile_size
-        for grid in self.grids:
-            for k, (y, x) in enumerate(grid):
-                for (y2, x2) in grid[k + 1:]:
-                    if abs(y - y2) < t and abs(x - x2) < t:
-                        return False
-        return True
+        # a grid is the product of its row and column starts: two tiles overlap iff they do on both axes, and two tiles
+        # of the same column (row) always exist for any pair of row (column) starts
+        def spaced(starts):
+            u = sorted(set(starts))
+            return all(b - a >= self.tile_size for a, b in zip(u, u[1:]))
+        return all(spaced([y for y, _ in g]) and spaced([x for _, x in g]) for g in self.grids)
 
     def tiles_per_image(self, num_steps: int) -> int:
         even = (num_steps + 1) // 2
