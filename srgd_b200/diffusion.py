@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Optional
 
 import torch
 import torch.nn as nn
