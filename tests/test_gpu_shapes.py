@@ -337,3 +337,29 @@ def test_unet_large_single_tiles_vs_oracle(B, H, W):
     err = (got - ref).abs()
     print(f"B={B} {H}x{W}: eps max-abs {float(err.max()):.5f} rms {float(err.pow(2).mean().sqrt()):.5f}")
     assert float(err.max()) < 6e-2 and float(err.pow(2).mean().sqrt()) < 1.2e-2
+
+
+def test_tiled_sample_minibatch_larger_than_the_tile_call_limit():
+    """tiled_sample(batch_size=128) on a 2304x2304 canvas: the 81 tiles of an even step are ONE minibatch (one noise
+    draw, one denoiser call of 81 rows, 162 with class guidance), above the 64-tile limit of a gather / scatter launch."""
+    from test_gpu_unet import _oracle_on_gpu
+    spec = O.UnetSpec(dim=64)
+    sd = O.make_state_dict(spec, 22, init="torch")
+    unet = M.ConditionalSRUnet(dim=64, learned_sinusoidal_cond=True, learned_sinusoidal_dim=32, num_classes=3)
+    diff = M.ConditionalContinuousTimeGaussianDiffusionSR(model=unet, image_size=256, num_sample_steps=250)
+    diff.load_state_dict(sd, strict=True)
+    diff = diff.eval().to("cuda")
+    diff.progress = False
+    gsd = _oracle_on_gpu(sd)
+    g = torch.Generator().manual_seed(19)
+    cond01 = torch.rand(1, 3, 2048, 2048, generator=g).cuda()
+    label = torch.tensor([1]).cuda()
+    kw = dict(class_cond_scale=2.0, num_sample_steps=250, generation_start_steps=246)
+    torch.manual_seed(71)
+    img = diff.tiled_sample(batch_size=128, condition_x=cond01, class_label=label, **kw)
+    torch.manual_seed(71)
+    with torch.inference_mode():
+        ref = O.tiled_sample(gsd, spec, 128, cond01, label, **kw)
+    err = float((img - ref).abs().max())
+    print(f"2304 canvas, batch_size 128, last 4 of 250 steps: max-abs {err:.5f}")
+    assert img.shape == (1, 3, 2048, 2048) and err <= 1e-2
