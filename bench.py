@@ -460,6 +460,9 @@ def main():
     import model as M
     from srgd_b200 import _lib, arch, sharding
 
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the product arm needs an sm_100 (B200) CUDA device -- there is no CPU fallback "
+                         "(`--impl reference` times the reference's algorithm on the host cores)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
